@@ -1,0 +1,195 @@
+"""Device plumbing: torch CUDA tensors as device-memory handles, the current torch stream, and thin
+Python wrappers (one per C-ABI entry point) that pass raw pointers to libqio_b200.so.
+
+PyTorch is used for allocation, streams and host<->device copies only -- every computation below
+is a call into the hand-written CUDA library.  No function here has a CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BLOCK_DOUBLES, LS_DTYPE, QioCudaError, check, lib
+
+F64 = torch.float64
+I32 = torch.int32
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise QioCudaError("qio_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def is_device(x) -> bool:
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def to_device(x, dtype=F64) -> torch.Tensor:
+    """numpy / list / torch (any device) -> contiguous CUDA tensor of ``dtype`` (no copy if already so)."""
+    dev = require_cuda()
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=dtype).contiguous()
+    arr = np.ascontiguousarray(np.asarray(x), dtype={F64: np.float64, I32: np.int32}[dtype])
+    return torch.from_numpy(arr).to(dev, non_blocking=False)
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+def like_input(t: torch.Tensor, template):
+    """Return ``t`` in the container type of ``template`` (numpy in -> numpy out, device in -> device out)."""
+    return t if is_device(template) else to_host(t)
+
+
+def _ptr(t) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def inactive_mask(inactive_indices, n: int) -> torch.Tensor:
+    """int32 mask of length n from the reference's list of inactive orbitals."""
+    m = np.zeros(n, dtype=np.int32)
+    idx = np.asarray(list(inactive_indices), dtype=np.int64)
+    if idx.size:
+        if idx.min() < 0 or idx.max() >= n:
+            raise IndexError("inactive index out of range")
+        m[idx] = 1
+    return to_device(m, I32)
+
+
+def empty(*shape, dtype=F64) -> torch.Tensor:
+    return torch.empty(*shape, dtype=dtype, device=require_cuda())
+
+
+# ---- one wrapper per entry point -----------------------------------------------------------------
+def prep_rdm12(dm1: torch.Tensor | None, dm2: torch.Tensor, n: int, na: int | None = None,
+               gamma: torch.Tensor | None = None, Gamma: torch.Tensor | None = None):
+    na = n if na is None else na
+    if dm1 is not None and gamma is None:
+        gamma = empty(2 * n, 2 * n)
+    if Gamma is None:
+        Gamma = empty(na, n, n, n)
+    check(lib.qio_b200_prep_rdm12(_ptr(dm1), _ptr(dm2), _ptr(gamma if dm1 is not None else None), _ptr(Gamma),
+                                   n, na, _stream()), 'prep_rdm12')
+    return gamma, Gamma
+
+
+def orbital_diagonals(gamma, Gamma, n, inds: torch.Tensor, a0=0, na=None) -> torch.Tensor:
+    na = n if na is None else na
+    m = int(inds.numel())
+    diag = empty(3, m)
+    check(lib.qio_b200_orbital_diagonals(_ptr(gamma), _ptr(Gamma), n, a0, na, _ptr(inds), m, _ptr(diag), _stream()),
+          'orbital_diagonals')
+    return diag
+
+
+def orbital_entropies(diag: torch.Tensor, want_spec=True, want_unmasked=False):
+    m = int(diag.shape[1])
+    spec = empty(4, m) if want_spec else None
+    s_masked = empty(m)
+    s_un = empty(m) if want_unmasked else None
+    summary = empty(4)
+    check(lib.qio_b200_orbital_entropies(_ptr(diag), m, _ptr(spec), _ptr(s_masked), _ptr(s_un), _ptr(summary),
+                                          _stream()), 'orbital_entropies')
+    return spec, s_masked, s_un, summary
+
+
+def shannon(p: torch.Tensor) -> torch.Tensor:
+    summary = empty(4)
+    check(lib.qio_b200_shannon(_ptr(p), int(p.numel()), _ptr(summary), _stream()), 'shannon')
+    return summary
+
+
+def pair_blocks(gamma, Gamma, n, pairs: torch.Tensor, a0=0, na=None) -> torch.Tensor:
+    na = n if na is None else na
+    P = int(pairs.shape[0])
+    blocks = empty(P, BLOCK_DOUBLES)
+    check(lib.qio_b200_pair_blocks(_ptr(gamma), _ptr(Gamma), n, a0, na, _ptr(pairs), P, _ptr(blocks), _stream()),
+          'pair_blocks')
+    return blocks
+
+
+def fqi_grad_hess(blocks, n, mask):
+    dX, ddX = empty(n, n), empty(n, n)
+    check(lib.qio_b200_fqi_grad_hess(_ptr(blocks), n, _ptr(mask), _ptr(dX), _ptr(ddX), _stream()), 'fqi_grad_hess')
+    return dX, ddX
+
+
+def pair_grad_hess(blocks, pairs, mask):
+    P = int(pairs.shape[0])
+    g1, g2 = empty(P), empty(P)
+    check(lib.qio_b200_pair_grad_hess(_ptr(blocks), _ptr(pairs), P, _ptr(mask), _ptr(g1), _ptr(g2), _stream()),
+          'pair_grad_hess')
+    return g1, g2
+
+
+def fqi_grad_hess_fused(gamma, Gamma, n, mask):
+    dX, ddX = empty(n, n), empty(n, n)
+    check(lib.qio_b200_fqi_grad_hess_fused(_ptr(gamma), _ptr(Gamma), n, _ptr(mask), _ptr(dX), _ptr(ddX), _stream()),
+          'fqi_grad_hess_fused')
+    return dX, ddX
+
+
+def pair_cost(blocks, cand_block, cand_pair, cand_cs, mask):
+    C = int(cand_block.numel())
+    cost = empty(C)
+    flags = empty(C, dtype=I32)
+    check(lib.qio_b200_pair_cost(_ptr(blocks), _ptr(cand_block), _ptr(cand_pair), _ptr(cand_cs), C, _ptr(mask),
+                                  _ptr(cost), _ptr(flags), _stream()), 'pair_cost')
+    return cost, flags
+
+
+def pair_linesearch(blocks, pairs, mask, tables) -> torch.Tensor:
+    P = int(pairs.shape[0])
+    results = torch.empty(P * LS_DTYPE.itemsize, dtype=torch.uint8, device=require_cuda())
+    check(lib.qio_b200_pair_linesearch(_ptr(blocks), _ptr(pairs), P, _ptr(mask), ctypes.byref(tables.struct),
+                                        _ptr(results), _stream()), 'pair_linesearch')
+    return results
+
+
+def results_to_numpy(results: torch.Tensor) -> np.ndarray:
+    return results.cpu().numpy().view(LS_DTYPE)
+
+
+def givens_apply(gamma, Gamma, n, i, j, c, s, zero_offspin=False):
+    check(lib.qio_b200_givens_apply(_ptr(gamma), _ptr(Gamma), n, int(i), int(j), float(c), float(s),
+                                     1 if zero_offspin else 0, _stream()), 'givens_apply')
+
+
+def rotate_rdm1(U, gamma, n) -> torch.Tensor:
+    out = torch.empty_like(gamma)
+    check(lib.qio_b200_rotate_rdm1(_ptr(U), _ptr(gamma), _ptr(out), n, _stream()), 'rotate_rdm1')
+    return out
+
+
+def rotate_rdm2_(U, Gamma, n, work=None) -> torch.Tensor:
+    """In place (needs an n^4 work buffer; allocated when not supplied)."""
+    if work is None:
+        work = torch.empty_like(Gamma)
+    check(lib.qio_b200_rotate_rdm2(_ptr(U), _ptr(Gamma), _ptr(work), n, _stream()), 'rotate_rdm2')
+    return Gamma
+
+
+def rotate_axis(U, src, dst, n, rows, ld_in):
+    check(lib.qio_b200_rotate_axis(_ptr(U), _ptr(src), _ptr(dst), n, int(rows), int(ld_in), _stream()), 'rotate_axis')
+    return dst
+
+
+def jacobi_cycle(gamma, Gamma, U, n, pairs, mask, tables):
+    P = int(pairs.shape[0])
+    results = torch.empty(max(P, 1) * LS_DTYPE.itemsize, dtype=torch.uint8, device=require_cuda())
+    summary = empty(4)
+    ws_bytes = int(lib.qio_b200_jacobi_workspace_bytes(n, P))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=require_cuda())
+    check(lib.qio_b200_jacobi_cycle(_ptr(gamma), _ptr(Gamma), _ptr(U), n, _ptr(pairs), P, _ptr(mask),
+                                     ctypes.byref(tables.struct), _ptr(results), _ptr(summary), _ptr(ws), _stream()),
+          'jacobi_cycle')
+    return results[:P * LS_DTYPE.itemsize], summary
