@@ -121,7 +121,7 @@ class QIO:
         return self.mo_coeff
 
 
-def upload_and_prep_rdm2(dm2: np.ndarray, n: int, a0: int = 0, na: int | None = None, slabs_per_chunk: int | None = None):
+def upload_and_prep_rdm2(dm2, n: int, a0: int = 0, na: int | None = None, slabs_per_chunk: int | None = None):
     """Host dm2[a0:a0+na] -> device Gamma[a0:a0+na] without ever holding the raw dm2 on the device:
     slabs of the leading index go through two pinned staging buffers on a copy stream while the prep
     kernel of the previous chunk runs (both permutations keep the leading index)."""
@@ -133,25 +133,32 @@ def upload_and_prep_rdm2(dm2: np.ndarray, n: int, a0: int = 0, na: int | None = 
     slab = n ** 3
     if slabs_per_chunk is None:
         slabs_per_chunk = max(1, min(na, (64 << 20) // (8 * slab) or 1))
-    src = np.ascontiguousarray(dm2[a0:a0 + na], dtype=np.float64).reshape(na, slab)
     compute = torch.cuda.current_stream()
     copy = torch.cuda.Stream()
-    pinned = [torch.empty((slabs_per_chunk, slab), dtype=torch.float64).pin_memory() for _ in range(2)]
     staged = [torch.empty((slabs_per_chunk, slab), dtype=torch.float64, device=d) for _ in range(2)]
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
-    host_free = [torch.cuda.Event() for _ in range(2)]
+    host_pinned = isinstance(dm2, torch.Tensor) and dm2.is_pinned() and dm2.is_contiguous() and dm2.dtype == torch.float64
+    if host_pinned:
+        src_t = dm2[a0:a0 + na].reshape(na, slab)      # caller-pinned memory: DMA straight out of it
+    else:
+        src = np.ascontiguousarray(np.asarray(dm2)[a0:a0 + na], dtype=np.float64).reshape(na, slab)
+        pinned = [torch.empty((slabs_per_chunk, slab), dtype=torch.float64).pin_memory() for _ in range(2)]
+        host_free = [torch.cuda.Event() for _ in range(2)]
+    copy.wait_stream(compute)
     for c, s0 in enumerate(range(0, na, slabs_per_chunk)):
         k = min(slabs_per_chunk, na - s0)
         b = c & 1
-        if c >= 2:
-            host_free[b].synchronize()           # pinned buffer b has been read by its H2D copy
-        pinned[b][:k].numpy()[...] = src[s0:s0 + k]
+        if not host_pinned:
+            if c >= 2:
+                host_free[b].synchronize()           # pinned buffer b has been read by its H2D copy
+            pinned[b][:k].numpy()[...] = src[s0:s0 + k]
         with torch.cuda.stream(copy):
             if c >= 2:
                 copy.wait_event(consumed[b])     # device staging buffer b has been consumed by its prep kernel
-            staged[b][:k].copy_(pinned[b][:k], non_blocking=True)
-            host_free[b].record(copy)
+            staged[b][:k].copy_(src_t[s0:s0 + k] if host_pinned else pinned[b][:k], non_blocking=True)
+            if not host_pinned:
+                host_free[b].record(copy)
             copied[b].record(copy)
         compute.wait_event(copied[b])
         dev.prep_rdm12(None, staged[b][:k], n, k, Gamma=Gamma[s0:s0 + k])
@@ -172,7 +179,7 @@ def prep_rdm12(dm1, dm2, on_device=False):
         gamma, Gamma = dev.prep_rdm12(d1, dm2.contiguous(), n)
         return gamma, Gamma
     gamma, _ = dev.prep_rdm12(d1, None, n, na=0, Gamma=dev.empty(0))
-    Gamma = upload_and_prep_rdm2(np.asarray(dm2), n)
+    Gamma = upload_and_prep_rdm2(dm2, n)
     if on_device:
         return gamma, Gamma
     return dev.to_host(gamma), dev.to_host(Gamma)
