@@ -266,6 +266,8 @@ def run_b200_arm(args):
     Gamma = dev.empty(n, n, n, n)
     gamma = dev.empty(2 * n, 2 * n)
     work = dev.empty(n, n, n, n)
+    W = dev.empty(n, n)
+    inds_d = dev.to_device(np.arange(n, dtype=np.int32), dev.I32)
     state = {}
 
     def device_step():
@@ -277,8 +279,13 @@ def run_b200_arm(args):
         dX, ddX = dev.fqi_grad_hess(blocks, n, mask)
         ls_all = dev.pair_linesearch(blocks, allpairs_d, mask, tabs)
         Ud = U0_d.clone()
-        res, summary = dev.jacobi_cycle(g, Gamma, Ud, n, pairs_d, mask, tabs)
-        state.update(ls_all=ls_all, res=res, summary=summary, U=Ud, dX=dX, g=g)
+        dev.sweep_reset(W, n)
+        res, summary = dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs)
+        diag = dev.deferred_diagonals(g, Gamma, W, n, inds_d)
+        _, _, _, esum = dev.orbital_entropies(diag, want_spec=False)
+        dev.zero_offspin_if_rotated(g, n, summary)
+        dev.sweep_flush(Gamma, W, n, work)
+        state.update(ls_all=ls_all, res=res, summary=summary, esum=esum, U=Ud, dX=dX, g=g)
 
     def count_evals():
         ra = dev.results_to_numpy(state['ls_all'])
@@ -302,7 +309,7 @@ def run_b200_arm(args):
         device_step()
     torch.cuda.synchronize()
     evals_per_step, n_accepted, rs = count_evals()
-    cost_after = float(dev.to_host(state['summary'])[1])
+    cost_after = float(dev.to_host(state['esum'])[0])
 
     # ---- timed: device-resident -----------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -319,7 +326,7 @@ def run_b200_arm(args):
     clocks = sampler.stop()
     ms_per_step = ms_total / args.steps
     value = evals_per_step / (ms_per_step * 1e-3)
-    launches_per_step = 2 + 1 + 4 + 1 + 1 + 1 + (1 + 2 * len(pairs_np) + 1)
+    launches_per_step = 2 + 1 + 4 + 1 + 1 + 1 + (1 + 1 + 1 + 1 + 1) + 3   # prep, rotations, all-pairs, sweep (+cost), flush
 
     # ---- phase timings (explain the step) and the roofline of the dominant kernel ----------------------
     def timed(fn, reps=1):
@@ -341,37 +348,46 @@ def run_b200_arm(args):
     phases['grad_hess_ms'] = timed(lambda: dev.fqi_grad_hess(blocks, n, mask), 5)
     phases['linesearch_all_pairs_ms'] = timed(lambda: dev.pair_linesearch(blocks, allpairs_d, mask, tabs), 5)
     Ud = U0_d.clone()
-    phases['jacobi_cycle_ms'] = timed(lambda: dev.jacobi_cycle(g, Gamma, Ud, n, pairs_d, mask, tabs), 1)
+    dev.sweep_reset(W, n)
+    sweep_ms = timed(lambda: dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs), 1)
+    phases['jacobi_cycle_kernel_ms'] = sweep_ms
+    rs2 = dev.results_to_numpy(dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs)[0])   # 3rd cycle: count below
+    phases['sweep_flush_ms'] = timed(lambda: dev.sweep_flush(Gamma, W, n, work), 1)
     m1_evals = int((1 + 314 + fine_len[np.where(dev.results_to_numpy(state['ls_all'])['coarse_index'] >= 0,
                                                 dev.results_to_numpy(state['ls_all'])['coarse_index'], 0)]).sum())
     phases['all_pairs_evals_per_s'] = m1_evals / (phases['linesearch_all_pairs_ms'] * 1e-3)
 
-    # dominant kernel = the Givens update; replay the accepted rotations of the sweep, alone, on the stream
-    acc = rs['accepted'] != 0
-    rot_pairs = pairs_np[acc]
-    rot_c, rot_s = rs['cos_theta'][acc], rs['sin_theta'][acc]
-    n_rep = min(len(rot_pairs), 400)
-    if n_rep:
-        def replay():
-            for k in range(n_rep):
-                dev.givens_apply(g, Gamma, n, rot_pairs[k][0], rot_pairs[k][1], rot_c[k], rot_s[k])
-        replay()
-        giv_ms = timed(replay, 1) / n_rep
-    else:
-        giv_ms = float('nan')
-    algo_bytes = 16.0 * (n ** 4 - (n - 2) ** 4)
+    # dominant kernel = the persistent sweep kernel.  Timed alone on the step's own first cycle (same start state).
+    dev.prep_rdm12(dm1_d, dm2_d, n, gamma=gamma, Gamma=Gamma)
+    g = dev.rotate_rdm1(U0_d, gamma, n)
+    dev.rotate_rdm2_(U0_d, Gamma, n, work)
+    Ud = U0_d.clone()
+    dev.sweep_reset(W, n)
+    sweep_ms = timed(lambda: dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs), 1)
+    phases['jacobi_cycle_kernel_first_cycle_ms'] = sweep_ms
+    tsum = dev.to_host(dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs)[1])
+    names = ['prologue', 'search_cta0', 'cta0_idle_tail', 'barrier1', 'superblock_and_barrier2', 'gather']
+    phases['sweep_phase_us_per_pair_cta0'] = {k: float(v) / 1e3 / len(pairs_np) for k, v in zip(names, tsum[4:10])}
+    lsn = ['coarse', 'reduce', 'fine', 'scan', 'margin', 'tail']
+    phases['linesearch_cycles_per_pair_cta0'] = {k: float(v) / len(pairs_np) for k, v in zip(lsn, tsum[10:16])}
+    algo_bytes = 16.0 * (n ** 4 - (n - 2) ** 4) * n_accepted      # bytes the reference update touches
+    kernel_bytes = 64.0 * n ** 3 * n_accepted + 32.0 * n * n * len(pairs_np)   # what the deferred layout moves
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
         peak = json.load(open(peaks_path))['hbm_gbs']
         peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)'
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-    achieved = algo_bytes / (giv_ms * 1e-3) / 1e9
-    roofline = {'kernel': 'givens_apply_kernel / sweep_givens_kernel (in-place 4-axis Givens rotation of rdm2)',
+    achieved = algo_bytes / (sweep_ms * 1e-3) / 1e9
+    roofline = {'kernel': 'sweep_v2_kernel (persistent Jacobi cycle: line searches + Givens updates of rdm2)',
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'peak_source': peak_src, 'traffic': None, 'algorithmic_bytes_per_launch': algo_bytes,
-                'avg_launch_ms': giv_ms, 'launches_timed': n_rep,
-                'note': 'per-rotation working set %.0f MB vs 126 MB L2' % (algo_bytes / 2e6)}
+                'avg_launch_ms': sweep_ms, 'launches_timed': 1,
+                'kernel_min_bytes_per_launch': kernel_bytes,
+                'kernel_min_bytes_frac': kernel_bytes / (sweep_ms * 1e-3) / 1e9 / peak,
+                'note': 'algorithmic bytes = 16 (n^4-(n-2)^4) per accepted rotation (SURVEY 8d); the deferred-axis layout '
+                        'moves only 64 n^3 B per rotation (+ 32 n^2 B of block rows per pair), see kernel_min_bytes_*; '
+                        'per-rotation working set %.0f MB vs 126 MB L2' % (32.0 * n ** 3 / 1e6)}
 
     # ---- e2e through the public API from pinned host memory ------------------------------------------------
     e2e = None

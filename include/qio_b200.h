@@ -134,10 +134,13 @@ int qio_b200_pair_cost(const double *blocks, const int32_t *cand_block, const in
 /* ---- a-5  qio/grad/jacobi.py:117-158  jacobi_direct, for P independent pairs ---------------
  * Sequential semantics reproduced exactly: strict '>' running minimum over the coarse grid,
  * fallback t_opt = 0.01, fine scan with the 1e-8 acceptance margin.  One CTA per pair, one
- * thread per angle.  blocks (P, 24) in the order of `pairs`. */
+ * thread per angle.  blocks (P, 24) in the order of `pairs`.  strict_order != 0 evaluates every
+ * candidate in the reference's own floating-point operation order (16-term sums, library log);
+ * 0 uses the polynomial form of the rotated occupations and a branch-free log (values agree to a few
+ * 1e-16; the returned angle can differ only when two candidates are that close, see the margins). */
 int qio_b200_pair_linesearch(const double *blocks, const int32_t *pairs, int P,
                              const int32_t *inactive, const qio_b200_theta_tables *h_tables,
-                             qio_b200_ls_result *results, void *stream);
+                             qio_b200_ls_result *results, int strict_order, void *stream);
 
 /* ---- a-6  qio/grad/jacobi.py:63-115  jacobi_transform --------------------------------------
  * In-place Givens rotation of orbitals (i, j) by (c, s) = (cos t, sin t) on all four axes of
@@ -160,6 +163,47 @@ int qio_b200_rotate_rdm2(const double *U, double *Gamma, double *work, int n, vo
  * the sharded rotation (the caller re-shards between passes). */
 int qio_b200_rotate_axis(const double *U, const double *in, double *out, int n, long long rows,
                          long long ld_in, void *stream);
+
+/* Single-axis contraction that keeps the index order (used to flush the deferred sweep state):
+ *   last_axis == 0:  out[i, m] = sum_a U[i, a] in[a, m]   in, out are (n, rows)
+ *   last_axis != 0:  out[m, i] = sum_d in[m, d] U[i, d]   in, out are (rows, n)              */
+int qio_b200_contract_axis(const double *U, const double *in, double *out, int n, long long rows,
+                           int last_axis, void *stream);
+
+/* ---- a-7 (deferred-axis form)  the Jacobi cycle as one persistent cooperative kernel ----------
+ * State: S with axes 1, 2 in the current basis and axes 0, 3 in the basis of the last flush, W (n, n)
+ * the rotation accumulated since:  Gamma[a,b,c,d] = sum W[a,a'] W[d,d'] S[a',b,c,d'].  A rank holds the
+ * slabs S[a0 : a0+na] of the (deferred) leading axis; gamma, U, W are replicated on every rank.
+ * sweep_reset sets W = 1 (S = Gamma then).  sweep_cycle runs the pair sequence exactly like
+ * qio_b200_jacobi_cycle (same result records) but touches only 64 n^3 B of S per accepted rotation, all
+ * row-contiguous and shard-local, and searches pair t+1 while pair t is being applied.  With peers, every
+ * rank calls it with the same arguments on its own shard; 256 doubles per pair are exchanged through
+ * peer-mapped mailboxes inside the kernel (no NCCL call on the path) and all ranks take identical decisions.
+ * summary (16) = [number accepted, unused, OR of flags, 0, then six phase timers of CTA 0 in ns, rest 0].
+ * deferred_diagonals is orbital_diagonals through the pending W (per-shard partial sums).  To obtain Gamma
+ * again: contract_axis(W, S -> work, leading) then contract_axis(W, work -> S, last), then sweep_reset. */
+typedef struct qio_b200_peers {
+    int32_t rank, nranks;
+    void *const *mailboxes; /* DEVICE array [nranks] of mailbox base pointers as mapped into THIS process
+                               (own + cudaIpc-opened peers); each mailbox has qio_b200_mailbox_bytes(nranks) */
+} qio_b200_peers;
+size_t qio_b200_sweep_workspace_bytes(int n);
+size_t qio_b200_mailbox_bytes(int nranks);
+int qio_b200_sweep_reset(double *W, int n, void *stream);
+int qio_b200_sweep_cycle(double *gamma, double *S, double *U, double *W, int n, int a0, int na,
+                         const int32_t *pairs, int P, const int32_t *inactive,
+                         const qio_b200_theta_tables *h_tables, qio_b200_ls_result *results, double *summary,
+                         void *workspace, const qio_b200_peers *h_peers, void *stream);
+int qio_b200_deferred_diagonals(const double *gamma, const double *S, const double *W, int n, int a0, int na,
+                                const int32_t *inds, int m, double *diag, void *stream);
+/* zeroes the up-down / down-up entries of gamma when summary[0] > 0 (the reference's jacobi_transform
+ * returns zeros there, qio/grad/jacobi.py:87). */
+int qio_b200_zero_offspin_if_rotated(double *gamma, int n, const double *summary, void *stream);
+/* cudaMalloc'ed, zeroed buffer + its 64-byte CUDA IPC handle; open / close a peer's; free one's own. */
+int qio_b200_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle64);
+int qio_b200_ipc_open(const unsigned char *handle64, void **ptr);
+int qio_b200_ipc_close(void *ptr);
+int qio_b200_ipc_free(void *ptr);
 
 /* ---- a-7  qio/grad/jacobi.py:211-233  one Jacobi cycle over a given pair sequence ------------
  * For each pair in order: line search on the CURRENT RDMs, and when an angle is accepted the

@@ -39,6 +39,11 @@ class ThetaTables(ctypes.Structure):
                 ('fine_cs', ctypes.c_void_p)]
 
 
+class Peers(ctypes.Structure):
+    """struct qio_b200_peers"""
+    _fields_ = [('rank', ctypes.c_int32), ('nranks', ctypes.c_int32), ('mailboxes', ctypes.c_void_p)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"qio_b200: CUDA library not built ({LIB_PATH} missing). Run `python -c 'import __graft_entry__ as g; "
@@ -64,11 +69,23 @@ SIGNATURES = {
     'qio_b200_pair_grad_hess': ([_p, _p, _i, _p, _p, _p, _p], _i),
     'qio_b200_fqi_grad_hess_fused': ([_p, _p, _i, _p, _p, _p, _p], _i),
     'qio_b200_pair_cost': ([_p, _p, _p, _p, _i, _p, _p, _p, _p], _i),
-    'qio_b200_pair_linesearch': ([_p, _p, _i, _p, ctypes.POINTER(ThetaTables), _p, _p], _i),
+    'qio_b200_pair_linesearch': ([_p, _p, _i, _p, ctypes.POINTER(ThetaTables), _p, _i, _p], _i),
     'qio_b200_givens_apply': ([_p, _p, _i, _i, _i, _d, _d, _i, _p], _i),
     'qio_b200_rotate_rdm1': ([_p, _p, _p, _i, _p], _i),
     'qio_b200_rotate_rdm2': ([_p, _p, _p, _i, _p], _i),
     'qio_b200_rotate_axis': ([_p, _p, _p, _i, _ll, _ll, _p], _i),
+    'qio_b200_contract_axis': ([_p, _p, _p, _i, _ll, _i, _p], _i),
+    'qio_b200_sweep_workspace_bytes': ([_i], ctypes.c_size_t),
+    'qio_b200_sweep_reset': ([_p, _i, _p], _i),
+    'qio_b200_mailbox_bytes': ([_i], ctypes.c_size_t),
+    'qio_b200_sweep_cycle': ([_p, _p, _p, _p, _i, _i, _i, _p, _i, _p, ctypes.POINTER(ThetaTables), _p, _p, _p,
+                              ctypes.POINTER(Peers), _p], _i),
+    'qio_b200_deferred_diagonals': ([_p, _p, _p, _i, _i, _i, _p, _i, _p, _p], _i),
+    'qio_b200_ipc_alloc': ([ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p], _i),
+    'qio_b200_ipc_open': ([ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)], _i),
+    'qio_b200_ipc_close': ([_p], _i),
+    'qio_b200_ipc_free': ([_p], _i),
+    'qio_b200_zero_offspin_if_rotated': ([_p, _i, _p, _p], _i),
     'qio_b200_jacobi_workspace_bytes': ([_i, _i], ctypes.c_size_t),
     'qio_b200_jacobi_cycle': ([_p, _p, _p, _i, _p, _i, _p, ctypes.POINTER(ThetaTables), _p, _p, _p, _p], _i),
 }

@@ -1,18 +1,21 @@
 // CTA-wide angle line search for ONE pair (reference qio/grad/jacobi.py:117-158), shared by the
-// batched all-pairs kernel (pairs.cu) and the sequential Jacobi sweep (sweep.cu).
+// batched all-pairs kernel (pairs.cu) and the Jacobi sweeps (sweep.cu, sweep2.cu).
 //
 // One thread per candidate angle.  The reference's sequential scans are reproduced exactly:
 //   coarse: running minimum with strict '>'  == first index of the global minimum, if it is
 //           strictly below cost(0); otherwise t_opt falls back to 0.01 == coarse point 0;
-//   fine:   accept k iff cost > cost_k + 1e-8, then cost = cost_k  (inherently sequential; one
-//           thread walks the <= 201 values that the CTA evaluated in parallel).
+//   fine:   accept k iff cost > cost_k + 1e-8, then cost = cost_k.  The chain is sequential in
+//           principle, but it decomposes into "find the first k beyond the last accepted one with
+//           cost_k + 1e-8 < cost" (a CTA-wide ballot) followed by a run of consecutive accepts
+//           (a_k := cost_{k-1} > cost_k + 1e-8, precomputed as a bit mask).  A smooth cost curve needs
+//           two rounds; any other sequence just takes more rounds with the same result.
 #pragma once
 #include "pair_math.cuh"
 
 namespace qio {
 
-constexpr int LS_THREADS = 320;           // >= 314 coarse points, 10 warps
-constexpr int LS_MAX_FINE = 256;          // capacity of the fine-value buffer
+constexpr int LS_THREADS = 320;           // >= 314 coarse points + 1, 10 warps
+constexpr int LS_MAX_FINE = 256;          // capacity of the fine-value buffers (8 warps x 32)
 
 struct ThetaTablesDev {                   // device copy of qio_b200_theta_tables (pointers are device pointers)
     int n_coarse, fine_stride;
@@ -33,102 +36,188 @@ static inline ThetaTablesDev to_dev(const qio_b200_theta_tables &t) {
     return d;
 }
 
-struct LineSearchSmem {
-    double fine_val[LS_MAX_FINE];
-    MinIdx warp_best[LS_THREADS / 32];
+template <int NT>
+struct LineSearchSmemT {
+    double fine_val[LS_MAX_FINE];     // cost at each fine angle
+    double fine_thr[LS_MAX_FINE];     // cost + 1e-8 (rounded add, as the reference's `new_cost + 1e-8`)
+    unsigned char accepted[LS_MAX_FINE];
+    unsigned amask[LS_MAX_FINE / 32]; // bit k: cost_{k-1} > cost_k + 1e-8
+    int wfirst[LS_MAX_FINE / 32];
+    MinIdx warp_best[NT / 32];
     MinIdx best;
+    double cost0;
+    double margin;
+    long long prof[8];                // cycles thread 0 spent per stage (coarse, reduce, fine, scan, margin, tail)
+    long long prof_last;
 };
+using LineSearchSmem = LineSearchSmemT<LS_THREADS>;
 
-// All LS_THREADS threads of the CTA must call this with the same arguments.  The result is
-// returned in every thread (res is filled identically) -- thread 0's scan is broadcast via smem.
-__device__ __forceinline__ void cta_linesearch(const PairBlock &b, bool i_in, bool j_in, const ThetaTablesDev &tab,
-                                               LineSearchSmem &sm, qio_b200_ls_result &res) {
+#define LS_PROF(k)                                  \
+    if (tid == 0) {                                 \
+        const long long now_ = clock64();           \
+        sm.prof[k] += now_ - sm.prof_last;          \
+        sm.prof_last = now_;                        \
+    }
+
+__device__ __forceinline__ double warp_min_double(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+// All NT threads of the CTA (NT >= LS_MAX_FINE) must call this with the same arguments.  The result is
+// returned in every thread (res is filled identically).  `b` is either a PairBlock / PairBlockRef
+// (reference operation order) or a PairCoef (fast polynomial form): pair_cost() is overloaded.
+template <int NT, typename Block>
+__device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool j_in, const ThetaTablesDev &tab,
+                                                 LineSearchSmemT<NT> &sm, qio_b200_ls_result &res) {
+    static_assert(NT >= LS_MAX_FINE && NT % 32 == 0, "line search needs at least 256 threads");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int flags = 0;
+    if (tid == 0) sm.prof_last = clock64();
 
-    // cost at theta = 0 with cos = 1, sin = 0 exactly as np.cos(0), np.sin(0)
-    const double cost0 = pair_cost(b, 1.0, 0.0, i_in, j_in, flags);
-
-    // ---- coarse grid ---------------------------------------------------------------------
+    // ---- coarse grid; candidate index n_coarse is theta = 0 (cos = 1, sin = 0 exactly as np.cos(0)) ----
     MinIdx mine;
     mine.v = INFINITY;
     mine.idx = 0x7fffffff;
     mine.v2 = INFINITY;
-    for (int t = tid; t < tab.n_coarse; t += LS_THREADS) {
-        const double2 cs = reinterpret_cast<const double2 *>(tab.coarse_cs)[t];
-        double v = pair_cost(b, cs.x, cs.y, i_in, j_in, flags);
-        if (!(v == v)) v = INFINITY;            // a NaN never wins a '>' comparison
-        MinIdx cand;
-        cand.v = v;
-        cand.idx = t;
-        cand.v2 = INFINITY;
-        mine = merge(mine, cand);
+    for (int t = tid; t <= tab.n_coarse; t += NT) {
+        if (t == tab.n_coarse) {
+            sm.cost0 = pair_cost(b, 1.0, 0.0, i_in, j_in, flags);
+        } else {
+            const double2 cs = reinterpret_cast<const double2 *>(tab.coarse_cs)[t];
+            double v = pair_cost(b, cs.x, cs.y, i_in, j_in, flags);
+            if (!(v == v)) v = INFINITY;            // a NaN never wins a '>' comparison
+            MinIdx cand;
+            cand.v = v;
+            cand.idx = t;
+            cand.v2 = INFINITY;
+            mine = merge(mine, cand);
+        }
     }
+    LS_PROF(0)
     mine = warp_min(mine);
     if (lane == 0) sm.warp_best[warp] = mine;
     __syncthreads();
     if (warp == 0) {
-        MinIdx x = (lane < LS_THREADS / 32) ? sm.warp_best[lane] : MinIdx{INFINITY, 0x7fffffff, INFINITY};
+        MinIdx x = (lane < NT / 32) ? sm.warp_best[lane] : MinIdx{INFINITY, 0x7fffffff, INFINITY};
         x = warp_min(x);
         if (lane == 0) sm.best = x;
     }
     __syncthreads();
     const MinIdx best = sm.best;
+    const double cost0 = sm.cost0;
     const bool improved = cost0 > best.v;
     const int row = improved ? best.idx : 0;
-    double cur = improved ? best.v : cost0;
+    const double start = improved ? best.v : cost0;
     const double coarse_margin = fmin(fabs(cost0 - best.v), best.v2 - best.v);
+    LS_PROF(1)
 
     // ---- fine grid of that coarse point ---------------------------------------------------
     const int L = min(tab.fine_len[row], LS_MAX_FINE);
     const double2 *fcs = reinterpret_cast<const double2 *>(tab.fine_cs) + (size_t)row * tab.fine_stride;
-    for (int t = tid; t < L; t += LS_THREADS) {
-        const double2 cs = fcs[t];
-        sm.fine_val[t] = pair_cost(b, cs.x, cs.y, i_in, j_in, flags);
-    }
-    const int any_warn = __syncthreads_or(flags & QIO_B200_FLAG_WARN_NEGATIVE);
-    const int any_raise = __syncthreads_or(flags & QIO_B200_FLAG_RAISE_GT1);
-
-    if (tid == 0) {
-        int fidx = -1;
-        double margin = INFINITY;
-#pragma unroll 8
-        for (int k = 0; k < L; ++k) {
-            const double v = sm.fine_val[k];
-            const double thr = __dadd_rn(v, 1e-8);
-            margin = fmin(margin, fabs(cur - thr));
-            if (cur > thr) {
-                cur = v;
-                fidx = k;
-            }
+    if (tid < LS_MAX_FINE) {
+        double v = INFINITY;
+        if (tid < L) {
+            const double2 cs = fcs[tid];
+            v = pair_cost(b, cs.x, cs.y, i_in, j_in, flags);
         }
-        // stash the scan result in the (now free) reduction slot
-        sm.best.v = cur;
-        sm.best.idx = fidx;
-        sm.best.v2 = margin;
+        sm.fine_val[tid] = v;
+        sm.fine_thr[tid] = __dadd_rn(v, 1e-8);      // +inf (or NaN) beyond L: never accepted
+        sm.accepted[tid] = 0;
+    }
+    const int any_flags = __syncthreads_or(flags);
+    LS_PROF(2)
+
+    // ---- the accept scan -----------------------------------------------------------------------
+    if (tid < LS_MAX_FINE) {
+        const bool a = tid > 0 && tid < L && sm.fine_val[tid - 1] > sm.fine_thr[tid];
+        const unsigned m = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) sm.amask[warp] = m;
     }
     __syncthreads();
-    const int fidx = sm.best.idx;
+    int last = -1;          // last accepted index (uniform over the CTA)
+    double cur = start;     // running cost (uniform)
+    for (;;) {
+        if (tid < LS_MAX_FINE) {
+            const bool pred = tid > last && sm.fine_thr[tid] < cur;     // tid < L implied (thr = +inf beyond)
+            const unsigned m = __ballot_sync(0xffffffffu, pred);
+            if (lane == 0) sm.wfirst[warp] = m ? (warp * 32 + __ffs(m) - 1) : 0x7fffffff;
+        }
+        __syncthreads();
+        int first = 0x7fffffff;
+#pragma unroll
+        for (int w = 0; w < LS_MAX_FINE / 32; ++w) first = min(first, sm.wfirst[w]);
+        if (first == 0x7fffffff) break;
+        // extend over the run of consecutive accepts that follows
+        int e = first;
+        while (e + 1 < L && ((sm.amask[(e + 1) >> 5] >> ((e + 1) & 31)) & 1u)) ++e;
+        if (tid >= first && tid <= e) sm.accepted[tid] = 1;
+        last = e;
+        cur = sm.fine_val[e];
+        __syncthreads();        // wfirst is rewritten in the next round
+    }
+    LS_PROF(3)
+
+    // ---- smallest |cost - (new_cost + 1e-8)| over every comparison of the reference's scan (warp 0) -------
+    __syncthreads();
+    if (warp == 0) {
+        constexpr int PER = LS_MAX_FINE / 32;
+        int chunk_last = -1;
+#pragma unroll
+        for (int e = 0; e < PER; ++e)
+            if (sm.accepted[lane * PER + e]) chunk_last = lane * PER + e;
+        int incl = chunk_last;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl = max(incl, t);
+        }
+        int prev = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) prev = -1;
+        double mg = INFINITY;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int k = lane * PER + e;
+            if (k < L) {
+                const double cb = prev >= 0 ? sm.fine_val[prev] : start;
+                mg = fmin(mg, fabs(cb - sm.fine_thr[k]));
+                if (sm.accepted[k]) prev = k;
+            }
+        }
+        mg = warp_min_double(mg);
+        if (lane == 0) sm.margin = mg;
+    }
+    __syncthreads();
+    LS_PROF(4)
+    const int fidx = last;
     res.coarse_index = improved ? best.idx : -1;
     res.fine_index = fidx;
-    res.flags = (any_warn ? QIO_B200_FLAG_WARN_NEGATIVE : 0) | (any_raise ? QIO_B200_FLAG_RAISE_GT1 : 0);
+    res.flags = any_flags & (QIO_B200_FLAG_WARN_NEGATIVE | QIO_B200_FLAG_RAISE_GT1);
     res.accepted = fidx >= 0 ? 1 : 0;
-    res.cost = sm.best.v;
+    res.cost = cur;
     res.cost0 = cost0;
     res.coarse_margin = coarse_margin;
-    res.fine_margin = sm.best.v2;
+    res.fine_margin = sm.margin;
     if (fidx >= 0) {
         const size_t e = (size_t)row * tab.fine_stride + fidx;
         res.theta = tab.fine_theta[e];
-        res.cos_theta = tab.fine_cs[2 * e];
-        res.sin_theta = tab.fine_cs[2 * e + 1];
+        const double2 cs = fcs[fidx];
+        res.cos_theta = cs.x;
+        res.sin_theta = cs.y;
     } else {
         res.theta = __longlong_as_double(0x7ff8000000000000LL);
         res.cos_theta = 1.0;
         res.sin_theta = 0.0;
     }
     res.reserved = 0.0;
+    LS_PROF(5)
     __syncthreads();   // smem may be reused by the caller
+}
+
+__device__ __forceinline__ void cta_linesearch(const PairBlock &b, bool i_in, bool j_in, const ThetaTablesDev &tab,
+                                               LineSearchSmem &sm, qio_b200_ls_result &res) {
+    cta_linesearch_t<LS_THREADS, PairBlock>(b, i_in, j_in, tab, sm, res);
 }
 
 }  // namespace qio

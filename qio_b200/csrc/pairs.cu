@@ -146,21 +146,35 @@ __global__ void pair_cost_kernel(const double *__restrict__ blocks, const int32_
 }
 
 // ---- batched line search: one CTA per pair -------------------------------------------------------
+template <bool STRICT>
 __global__ void __launch_bounds__(LS_THREADS)
     pair_linesearch_kernel(const double *__restrict__ blocks, const int32_t *__restrict__ pairs, int P,
                            const int32_t *__restrict__ inactive, ThetaTablesDev tab,
                            qio_b200_ls_result *__restrict__ results) {
     __shared__ LineSearchSmem sm;
     __shared__ double rec[QIO_B200_BLOCK_DOUBLES];
+    __shared__ PairCoef pc;
+    __shared__ double2 coarse_cs_sm[320];
+    if (tab.n_coarse <= 320) {      // the coarse cos/sin table is reused for every pair of this CTA
+        for (int t = threadIdx.x; t < tab.n_coarse; t += LS_THREADS)
+            coarse_cs_sm[t] = reinterpret_cast<const double2 *>(tab.coarse_cs)[t];
+        tab.coarse_cs = reinterpret_cast<const double *>(coarse_cs_sm);
+    }
     for (int p = blockIdx.x; p < P; p += gridDim.x) {
         if (threadIdx.x < QIO_B200_BLOCK_DOUBLES)
             rec[threadIdx.x] = blocks[(size_t)p * QIO_B200_BLOCK_DOUBLES + threadIdx.x];
         __syncthreads();
-        PairBlock b;
-        load_block(rec, b);
         const int i = pairs[2 * p], j = pairs[2 * p + 1];
         qio_b200_ls_result res;
-        cta_linesearch(b, inactive[i] != 0, inactive[j] != 0, tab, sm, res);
+        if (STRICT) {
+            PairBlock b;
+            load_block(rec, b);
+            cta_linesearch(b, inactive[i] != 0, inactive[j] != 0, tab, sm, res);
+        } else {
+            if (threadIdx.x == 0) make_coef(rec, pc);
+            __syncthreads();
+            cta_linesearch_t<LS_THREADS, PairCoef>(pc, inactive[i] != 0, inactive[j] != 0, tab, sm, res);
+        }
         if (threadIdx.x == 0) results[p] = res;
     }
 }
@@ -236,7 +250,7 @@ extern "C" int qio_b200_pair_cost(const double *blocks, const int32_t *cand_bloc
 
 extern "C" int qio_b200_pair_linesearch(const double *blocks, const int32_t *pairs, int P, const int32_t *inactive,
                                         const qio_b200_theta_tables *h_tables, qio_b200_ls_result *results,
-                                        void *stream) {
+                                        int strict_order, void *stream) {
     using namespace qio;
     QIO_REQUIRE(P >= 0, "pair_linesearch: bad size");
     if (P == 0) return QIO_B200_OK;
@@ -245,7 +259,10 @@ extern "C" int qio_b200_pair_linesearch(const double *blocks, const int32_t *pai
                 "pair_linesearch: table sizes out of range");
     // persistent grid: a multiple of the SM count (6 CTAs of 320 threads fit per SM)
     const int grid = min(P, sm_count() * 6);
-    pair_linesearch_kernel<<<grid, LS_THREADS, 0, as_stream(stream)>>>(blocks, pairs, P, inactive, to_dev(*h_tables), results);
+    if (strict_order)
+        pair_linesearch_kernel<true><<<grid, LS_THREADS, 0, as_stream(stream)>>>(blocks, pairs, P, inactive, to_dev(*h_tables), results);
+    else
+        pair_linesearch_kernel<false><<<grid, LS_THREADS, 0, as_stream(stream)>>>(blocks, pairs, P, inactive, to_dev(*h_tables), results);
     QIO_LAUNCH_CHECK();
     return QIO_B200_OK;
 }

@@ -36,11 +36,12 @@ __global__ void __launch_bounds__(LS_THREADS)
         const size_t off = block_entry_offset(threadIdx.x, i, j, n);
         rec[threadIdx.x] = (threadIdx.x < 16) ? Gamma[off] : gamma[off];
     }
+    __shared__ PairCoef pc;
     __syncthreads();
-    PairBlock b;
-    load_block(rec, b);
+    if (threadIdx.x == 0) make_coef(rec, pc);
+    __syncthreads();
     qio_b200_ls_result res;
-    cta_linesearch(b, inactive[i] != 0, inactive[j] != 0, tab, sm, res);
+    cta_linesearch_t<LS_THREADS, PairCoef>(pc, inactive[i] != 0, inactive[j] != 0, tab, sm, res);
     if (threadIdx.x == 0) {
         results[step] = res;
         sc->params.i = i;

@@ -147,11 +147,11 @@ def pair_cost(blocks, cand_block, cand_pair, cand_cs, mask):
     return cost, flags
 
 
-def pair_linesearch(blocks, pairs, mask, tables) -> torch.Tensor:
+def pair_linesearch(blocks, pairs, mask, tables, strict_order=False) -> torch.Tensor:
     P = int(pairs.shape[0])
     results = torch.empty(P * LS_DTYPE.itemsize, dtype=torch.uint8, device=require_cuda())
     check(lib.qio_b200_pair_linesearch(_ptr(blocks), _ptr(pairs), P, _ptr(mask), ctypes.byref(tables.struct),
-                                        _ptr(results), _stream()), 'pair_linesearch')
+                                        _ptr(results), 1 if strict_order else 0, _stream()), 'pair_linesearch')
     return results
 
 
@@ -193,3 +193,52 @@ def jacobi_cycle(gamma, Gamma, U, n, pairs, mask, tables):
                                      ctypes.byref(tables.struct), _ptr(results), _ptr(summary), _ptr(ws), _stream()),
           'jacobi_cycle')
     return results[:P * LS_DTYPE.itemsize], summary
+
+
+def contract_axis(U, src, dst, n, rows, last_axis):
+    check(lib.qio_b200_contract_axis(_ptr(U), _ptr(src), _ptr(dst), n, int(rows), 1 if last_axis else 0, _stream()),
+          'contract_axis')
+    return dst
+
+
+def sweep_reset(W, n):
+    check(lib.qio_b200_sweep_reset(_ptr(W), n, _stream()), 'sweep_reset')
+
+
+def sweep_cycle(gamma, S, U, W, n, pairs, mask, tables, a0=0, na=None, peers=None):
+    """One cycle on the deferred-axis state (S, W); returns (results bytes, summary).
+    ``peers`` is a qio_b200.peers.PeerGroup (multi-GPU) or None."""
+    na = n if na is None else na
+    P = int(pairs.shape[0])
+    results = torch.empty(max(P, 1) * LS_DTYPE.itemsize, dtype=torch.uint8, device=require_cuda())
+    summary = empty(16)
+    ws = torch.empty(int(lib.qio_b200_sweep_workspace_bytes(n)), dtype=torch.uint8, device=require_cuda())
+    check(lib.qio_b200_sweep_cycle(_ptr(gamma), _ptr(S), _ptr(U), _ptr(W), n, a0, na, _ptr(pairs), P, _ptr(mask),
+                                    ctypes.byref(tables.struct), _ptr(results), _ptr(summary), _ptr(ws),
+                                    ctypes.byref(peers.struct) if peers is not None else None, _stream()),
+          'sweep_cycle')
+    return results[:P * LS_DTYPE.itemsize], summary
+
+
+def deferred_diagonals(gamma, S, W, n, inds, a0=0, na=None):
+    na = n if na is None else na
+    m = int(inds.numel())
+    diag = empty(3, m)
+    check(lib.qio_b200_deferred_diagonals(_ptr(gamma), _ptr(S), _ptr(W), n, a0, na, _ptr(inds), m, _ptr(diag),
+                                           _stream()), 'deferred_diagonals')
+    return diag
+
+
+def zero_offspin_if_rotated(gamma, n, summary):
+    check(lib.qio_b200_zero_offspin_if_rotated(_ptr(gamma), n, _ptr(summary), _stream()), 'zero_offspin_if_rotated')
+
+
+def sweep_flush(S, W, n, work=None):
+    """Gamma = W applied to axes 0 and 3 of S (two DMMA GEMM passes), result in S; W reset to 1."""
+    if work is None:
+        work = torch.empty_like(S)
+    n3 = n ** 3
+    contract_axis(W, S, work, n, n3, last_axis=False)
+    contract_axis(W, work, S, n, n3, last_axis=True)
+    sweep_reset(W, n)
+    return S

@@ -61,14 +61,15 @@ def jacobi_transform(gamma, Gamma, i, j, t):
     return dev.like_input(g, gamma), dev.like_input(G, Gamma)
 
 
-def linesearch_pairs(gamma, Gamma, pairs, inactive_indices):
+def linesearch_pairs(gamma, Gamma, pairs, inactive_indices, strict_order=False):
     """Line search for many INDEPENDENT pairs on the same RDMs (the batched form of jacobi_direct).
-    Returns the structured result array (see _lib.LS_DTYPE), one record per pair."""
+    Returns the structured result array (see _lib.LS_DTYPE), one record per pair.
+    ``strict_order`` evaluates every candidate in the reference's own floating-point operation order."""
     n = int(Gamma.shape[0])
     g, G = dev.to_device(gamma), dev.to_device(Gamma)
     p = dev.to_device(np.asarray(pairs, dtype=np.int32).reshape(-1, 2), dev.I32)
     blocks = dev.pair_blocks(g, G, n, p)
-    res = dev.pair_linesearch(blocks, p, dev.inactive_mask(inactive_indices, n), device_tables())
+    res = dev.pair_linesearch(blocks, p, dev.inactive_mask(inactive_indices, n), device_tables(), strict_order)
     return dev.results_to_numpy(res)
 
 
@@ -103,13 +104,48 @@ def random_start(n):
     return expm(X)
 
 
-def run_cycle(g, G, Ud, n, pairs_np, mask, tables):
-    """One device-resident Jacobi cycle. Returns (records, n_accepted, cost_after, flags)."""
-    pairs = dev.to_device(pairs_np, dev.I32)
-    results, summary = dev.jacobi_cycle(g, G, Ud, n, pairs, mask, tables)
-    rec = dev.results_to_numpy(results)
-    n_acc, cost, flags, _ = dev.to_host(summary)
-    return rec, int(n_acc), float(cost), int(flags)
+# Which device implementation of the cycle runs: 'deferred' = one persistent kernel on the deferred-axis
+# state (S, W) (sweep2.cu, the fast path); 'materialized' = one search + one Givens launch per pair on the
+# fully materialised 2-RDM (sweep.cu, kept as an independent cross-check).
+ENGINE = 'deferred'
+
+
+class SweepState:
+    """Device-resident state of a Jacobi optimisation: gamma, the 2-RDM (materialised or deferred), U."""
+
+    def __init__(self, g, G, Ud, n, inactive_indices, engine=None):
+        self.g, self.G, self.U, self.n = g, G, Ud, n
+        self.engine = engine or ENGINE
+        self.mask = dev.inactive_mask(inactive_indices, n)
+        self.inds = dev.to_device(np.asarray(list(inactive_indices), dtype=np.int32), dev.I32)
+        self.tables = device_tables()
+        self.W = None
+        if self.engine == 'deferred':
+            self.W = dev.empty(n, n)
+            dev.sweep_reset(self.W, n)
+
+    def cycle(self, pairs_np):
+        """Run one cycle over ``pairs_np``. Returns (records, n_accepted, cost_after, flags)."""
+        n = self.n
+        pairs = dev.to_device(pairs_np, dev.I32)
+        if self.engine == 'deferred':
+            results, summary = dev.sweep_cycle(self.g, self.G, self.U, self.W, n, pairs, self.mask, self.tables)
+            diag = dev.deferred_diagonals(self.g, self.G, self.W, n, self.inds)
+            _, _, _, esum = dev.orbital_entropies(diag, want_spec=False)
+            dev.zero_offspin_if_rotated(self.g, n, summary)
+            n_acc, _, flags = dev.to_host(summary)[:3]
+            cost, _, _, eflags = dev.to_host(esum)
+            flags = int(flags) | int(eflags)
+        else:
+            results, summary = dev.jacobi_cycle(self.g, self.G, self.U, n, pairs, self.mask, self.tables)
+            n_acc, cost, flags, _ = dev.to_host(summary)
+        return dev.results_to_numpy(results), int(n_acc), float(cost), int(flags)
+
+    def finish(self, work=None):
+        """Materialise the 2-RDM (applies the pending rotation of the deferred engine)."""
+        if self.engine == 'deferred':
+            dev.sweep_flush(self.G, self.W, self.n, work)
+        return self.g, self.G
 
 
 def minimize_orb_corr_jacobi(gamma, Gamma, inactive_indices, max_cycle):
@@ -120,13 +156,13 @@ def minimize_orb_corr_jacobi(gamma, Gamma, inactive_indices, max_cycle):
     n = int(Gamma.shape[0])
     g = dev.to_device(gamma).clone()
     G = dev.to_device(Gamma).clone()
-    mask = dev.inactive_mask(inactive_indices, n)
-    tables = device_tables()
+    work = torch_empty_like(G)
 
     U0 = random_start(n)
     Ud = dev.to_device(U0).clone()
     g = dev.rotate_rdm1(Ud, g, n)
-    dev.rotate_rdm2_(Ud, G, n)
+    dev.rotate_rdm2_(Ud, G, n, work)
+    state = SweepState(g, G, Ud, n, inactive_indices)
 
     rotations = []
     logger.info('Optimizig Orbitals...')
@@ -137,7 +173,7 @@ def minimize_orb_corr_jacobi(gamma, Gamma, inactive_indices, max_cycle):
         orb_list = np.arange(0, n)
         np.random.shuffle(orb_list)
         pairs = sweep_pairs(orb_list, inactive_indices)
-        rec, n_acc, cost_after, flags = run_cycle(g, G, Ud, n, pairs, mask, tables)
+        rec, n_acc, cost_after, flags = state.cycle(pairs)
         if flags:
             raise_or_warn(flags)
         acc = rec['accepted'] != 0
@@ -156,7 +192,13 @@ def minimize_orb_corr_jacobi(gamma, Gamma, inactive_indices, max_cycle):
         cycle_cost = new_cost
         logger.info('cost= %s', cycle_cost)
 
+    g, G = state.finish(work)
     return rotations, dev.to_host(Ud), dev.like_input(g, gamma), dev.like_input(G, Gamma)
+
+
+def torch_empty_like(t):
+    import torch
+    return torch.empty_like(t)
 
 
 # ---------------------------------------------------------------------------------------------------

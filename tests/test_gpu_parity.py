@@ -111,13 +111,14 @@ def test_jacobi_cost_golden(golden):
                 assert abs(JA.jacobi_cost(t, int(i), int(j), gd, Gd, inact) - v) < ENT_TOL
 
 
-def test_jacobi_direct_golden_angles_bit_exact(golden):
+@pytest.mark.parametrize('strict', [False, True])
+def test_jacobi_direct_golden_angles_bit_exact(golden, strict):
     gam, Gam = rebuild_inputs(golden)
     gd, Gd = dev.to_device(gam), dev.to_device(Gam)
     for name in ('all', 'partial'):
         inact = golden[f'inactive_{name}'].tolist()
         pairs, want = golden[f'ls_pairs_{name}'], golden[f'ls_theta_{name}']
-        rec = JA.linesearch_pairs(gd, Gd, pairs, inact)
+        rec = JA.linesearch_pairs(gd, Gd, pairs, inact, strict_order=strict)
         got = np.where(rec['accepted'] != 0, rec['theta'], np.nan)
         assert np.array_equal(got, want, equal_nan=True)
         # the scalar API on a few pairs
@@ -126,12 +127,13 @@ def test_jacobi_direct_golden_angles_bit_exact(golden):
             assert (t is None and np.isnan(t_ref)) or t == t_ref
 
 
-def test_linesearch_all_pairs_vs_oracle_n40():
+@pytest.mark.parametrize('strict', [False, True])
+def test_linesearch_all_pairs_vs_oracle_n40(strict):
     n = 40
     g, G = rotated_case(n)
     inact = [0, 1] + list(range(10, n))
     pairs = [(i, j) for i in range(n) for j in range(i) if (i in inact or j in inact)]
-    rec = JA.linesearch_pairs(g, G, pairs, inact)
+    rec = JA.linesearch_pairs(g, G, pairs, inact, strict_order=strict)
     close = 0
     for (i, j), r in zip(pairs, rec):
         info = O.jacobi_direct(i, j, g, G, inact, details=True)
@@ -141,6 +143,7 @@ def test_linesearch_all_pairs_vs_oracle_n40():
         assert r['coarse_index'] == info['coarse_index'] and r['fine_index'] == info['fine_index']
         assert (info['theta'] is None and not r['accepted']) or r['theta'] == info['theta']
         assert abs(r['cost'] - info['cost']) < ENT_TOL and abs(r['cost0'] - info['cost0']) < ENT_TOL
+        assert abs(r['fine_margin'] - info['fine_margin']) < 1e-12
     assert close <= 2
 
 
@@ -283,7 +286,50 @@ def test_newton_driver_golden(golden6, golden12):
 
 
 # ---- a-7 ------------------------------------------------------------------------------------------
-def test_jacobi_driver_golden_rotations_bit_exact(golden):
+@pytest.mark.parametrize('n,rows', [(6, 216), (12, 100), (17, 60), (28, 28 ** 3)])
+def test_contract_axis_keep_order(n, rows):
+    rng = np.random.default_rng(n)
+    U = rng.standard_normal((n, n))
+    lead = rng.standard_normal((n, rows))
+    out = dev.contract_axis(dev.to_device(U), dev.to_device(lead), dev.empty(n, rows), n, rows, last_axis=False)
+    assert np.allclose(dev.to_host(out), U @ lead, atol=1e-11, rtol=1e-12)
+    last = rng.standard_normal((rows, n))
+    out = dev.contract_axis(dev.to_device(U), dev.to_device(last), dev.empty(rows, n), n, rows, last_axis=True)
+    assert np.allclose(dev.to_host(out), last @ U.T, atol=1e-11, rtol=1e-12)
+
+
+@pytest.mark.parametrize('n', [5, 12, 28])
+def test_deferred_engine_matches_materialized_engine(n):
+    """The persistent deferred-axis cycle and the per-pair materialised cycle are independent device
+    implementations: same accept / reject pattern and angles, same RDMs after the flush."""
+    g, G = rotated_case(n, seed=3, np_seed=4)
+    inact = [0, 1] + list(range(3, n))
+    order = np.random.default_rng(n).permutation(n)
+    pairs = JA.sweep_pairs(order, inact)
+    out = {}
+    for engine in ('materialized', 'deferred'):
+        gd, Gd, Ud = dev.to_device(g).clone(), dev.to_device(G).clone(), dev.to_device(np.eye(n)).clone()
+        st = JA.SweepState(gd, Gd, Ud, n, inact, engine=engine)
+        rec1, acc1, cost1, _ = st.cycle(pairs)
+        rec2, acc2, cost2, _ = st.cycle(pairs[::-1].copy())          # second cycle on the deferred state
+        gg, GG = st.finish()
+        out[engine] = (rec1, rec2, cost1, cost2, dev.to_host(gg), dev.to_host(GG), dev.to_host(Ud))
+    a, b = out['materialized'], out['deferred']
+    for k in (0, 1):
+        assert np.array_equal(a[k]['accepted'], b[k]['accepted'])
+        assert np.array_equal(a[k]['theta'], b[k]['theta'], equal_nan=True)
+        assert np.allclose(a[k]['cost'], b[k]['cost'], atol=1e-12, rtol=0)
+    assert abs(a[2] - b[2]) < 1e-12 and abs(a[3] - b[3]) < 1e-12
+    assert np.allclose(a[4], b[4], atol=1e-12, rtol=0) and np.allclose(a[5], b[5], atol=1e-12, rtol=0)
+    assert np.allclose(a[6], b[6], atol=1e-12, rtol=0)
+    # and both agree with rotating the input by the accumulated U
+    assert np.allclose(b[5], O.rotate_rdm2(b[6], G), atol=1e-11, rtol=0)
+    assert abs(get_cost_fqi(b[4], b[5], inact) - b[3]) < 1e-12
+
+
+@pytest.mark.parametrize('engine', ['deferred', 'materialized'])
+def test_jacobi_driver_golden_rotations_bit_exact(golden, engine, monkeypatch):
+    monkeypatch.setattr(JA, 'ENGINE', engine)
     gamma0, Gamma0 = prepared_inputs(golden)
     n = int(golden['n'])
     for name in ('all', 'partial'):
