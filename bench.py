@@ -231,9 +231,7 @@ def run_b200_arm(args):
     from qio_b200.qio import prep_rdm12
 
     if world > 1:
-        from qio_b200 import sharded
-        return sharded.bench_arm(args, rank, world, local_rank, workload_config, sweep_order, ClockSampler,
-                                 cpu_reference_sample, METRIC, UNIT)
+        return run_b200_multi(args, rank, world, local_rank)
 
     n = args.n
     P = n * (n - 1) // 2
@@ -419,6 +417,143 @@ def run_b200_arm(args):
         'phases': phases,
     }
     print(json.dumps(out))
+
+
+def run_b200_multi(args, rank, world, local_rank):
+    """N > 1: rdm2 sharded by leading index, one process per GPU (qio_b200.sharded).  Same step as the 1-GPU arm."""
+    import torch
+    import torch.distributed as dist
+
+    from qio_b200 import device as dev
+    from qio_b200 import synth, tables
+    from qio_b200._lib import LS_DTYPE
+    from qio_b200.grad import jacobi as JA
+    from qio_b200.peers import PeerGroup
+    from qio_b200.sharded import ShardedRDM, shard_range
+
+    n = args.n
+    P = n * (n - 1) // 2
+    inact = list(range(n))
+    a0, a1 = shard_range(n, rank, world)
+    na = a1 - a0
+    # this rank's slabs of the synthetic solver output, on the device and in pinned host memory
+    w, Pk = synth.projectors(n)
+    d1 = 2.0 * torch.from_numpy(Pk).cuda()
+    wt = torch.from_numpy(w).cuda()
+    dm1_d = torch.einsum('k,kab->ab', wt, d1).contiguous()
+    dm2_d = torch.zeros((na, n, n, n), dtype=torch.float64, device='cuda')
+    for k in range(len(w)):     # input synthesis only (plumbing, outside every timed region)
+        dl = d1[k][a0:a1]
+        dm2_d += wt[k] * (torch.einsum('pq,rs->pqrs', dl, d1[k]) - 0.5 * torch.einsum('ps,rq->pqrs', dl, d1[k]))
+    dm2_h = torch.empty((na, n, n, n), dtype=torch.float64).pin_memory()
+    dm2_h.copy_(dm2_d)
+    dm1_h = dm1_d.cpu().numpy()
+    torch.cuda.synchronize()
+
+    U0, order = sweep_order(n)
+    pairs_np = JA.sweep_pairs(order, inact)
+    U0_d = dev.to_device(U0)
+    mask = dev.inactive_mask(inact, n)
+    inds_d = dev.to_device(np.arange(n, dtype=np.int32), dev.I32)
+    tabs = tables.device_tables()
+    fine_len = tabs.host['fine_len']
+    peers = PeerGroup()
+    W = dev.empty(n, n)
+    work_full = dev.empty(n, n, n, n)
+    state = {}
+
+    def step(dm1_in, dm2_in):
+        st = ShardedRDM.from_solver(dm1_in, dm2_in, n, peers=peers)
+        st.rotate_(U0_d, work_full)
+        dX, ddX, rec_all = st.all_pairs_pass(inact, tabs)
+        Ud = U0_d.clone()
+        dev.sweep_reset(W, n)
+        rec, n_acc, cost, flags = st.sweep_cycle(Ud, W, pairs_np, mask, inds_d, tabs)
+        st.flush(W, work_full)
+        state.update(rec_all=rec_all, rec=rec, n_acc=n_acc, cost=cost, U=Ud, st=st)
+
+    for _ in range(max(args.warmup, 3)):
+        step(dm1_d, dm2_d)
+    torch.cuda.synchronize()
+    ra = state['rec_all'].cpu().numpy().view(LS_DTYPE)
+    rs = state['rec']
+    rows_a = np.where(ra['coarse_index'] >= 0, ra['coarse_index'], 0)
+    rows_s = np.where(rs['coarse_index'] >= 0, rs['coarse_index'], 0)
+    evals_per_step = int((1 + 314 + fine_len[rows_a]).sum() + (1 + 314 + fine_len[rows_s]).sum())
+
+    def timed_steps(dm1_in, dm2_in, k):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.5)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(k):
+            step(dm1_in, dm2_in)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / k, sampler.stop()
+
+    ms_per_step, clocks = timed_steps(dm1_d, dm2_d, args.steps)
+    value = evals_per_step / (ms_per_step * 1e-3)
+    e2e = None
+    if not args.no_e2e:
+        step(dm1_h, dm2_h)
+        e2e_ms, _ = timed_steps(dm1_h, dm2_h, args.steps)
+        e2e = {'value': evals_per_step / (e2e_ms * 1e-3), 'unit': UNIT,
+               'h2d_bytes_per_step': int(8 * (n ** 4 + n ** 2) + 8 * (len(pairs_np) + P)),
+               'd2h_bytes_per_step': int(LS_DTYPE.itemsize * (len(pairs_np) + P) + 64 * world), 'ms_per_step': e2e_ms,
+               'api': 'qio_b200.sharded.ShardedRDM.from_solver(host dm1, pinned host dm2 shard) -> rotate_ -> all_pairs_pass '
+                      '-> sweep_cycle -> flush on every rank; records read back'}
+
+    # the sweep kernel alone (dominant kernel), from the step's own start state
+    st = ShardedRDM.from_solver(dm1_d, dm2_d, n, peers=peers)
+    st.rotate_(U0_d, work_full)
+    Ud = U0_d.clone()
+    dev.sweep_reset(W, n)
+    pairs_d = dev.to_device(pairs_np, dev.I32)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _, summ = dev.sweep_cycle(st.gamma, st.G, Ud, W, n, pairs_d, mask, tabs, st.a0, st.na, peers)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sweep_ms = float(t.item())
+    tsum = dev.to_host(summ)
+    n_acc = int(tsum[0])
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    peak = json.load(open(peaks_path))['hbm_gbs'] if os.path.exists(peaks_path) else 6650.0
+    algo_bytes = 16.0 * (n ** 4 - (n - 2) ** 4) * n_acc / world
+    achieved = algo_bytes / (sweep_ms * 1e-3) / 1e9
+    names = ['prologue', 'search_cta0', 'cta0_idle_tail', 'barrier1', 'superblock_and_barrier2', 'gather']
+    roofline = {'kernel': 'sweep_kernel (persistent Jacobi cycle), per GPU', 'bound': 'hbm', 'achieved': achieved,
+                'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'algorithmic_bytes_per_launch': algo_bytes, 'avg_launch_ms': sweep_ms, 'launches_timed': 1,
+                'kernel_min_bytes_per_launch': (64.0 * n ** 3 * n_acc + 32.0 * n * n * len(pairs_np)) / world,
+                'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if os.path.exists(peaks_path) else 'fallback',
+                'note': 'per-GPU share of the algorithmic bytes (16 (n^4-(n-2)^4) per accepted rotation / n_gpus) over the '
+                        'slowest rank\'s kernel time'}
+    if rank == 0:
+        out = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(n, world),
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': (2 + 1 + 3 * na + 1 + 1 + 2 + 5 + 3) * args.steps,
+            'roofline': roofline, 'cpu_baseline': None, 'evals_per_step': evals_per_step,
+            'rotations_accepted': n_acc, 'cost_after_cycle': state['cost'],
+            'phases': {'jacobi_cycle_kernel_ms': sweep_ms,
+                       'sweep_phase_us_per_pair_cta0': {k: float(v) / 1e3 / len(pairs_np) for k, v in zip(names, tsum[4:10])}},
+        }
+        print(json.dumps(out))
+    peers.close()
+    dist.destroy_process_group()
 
 
 def main():

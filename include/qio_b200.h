@@ -170,6 +170,12 @@ int qio_b200_rotate_axis(const double *U, const double *in, double *out, int n, 
 int qio_b200_contract_axis(const double *U, const double *in, double *out, int n, long long rows,
                            int last_axis, void *stream);
 
+/* Partial leading-axis contraction over a shard of the contracted index (multi-GPU rotation / flush):
+ *   out[i, m] = sum_{k < kdim} U[i * ldu + k] in[k, m],   in (kdim, rows), out (n, rows);
+ * the ranks' outputs are summed by a reduce-scatter. */
+int qio_b200_contract_axis_partial(const double *U, long long ldu, const double *in, double *out, int n,
+                                   int kdim, long long rows, void *stream);
+
 /* ---- a-7 (deferred-axis form)  the Jacobi cycle as one persistent cooperative kernel ----------
  * State: S with axes 1, 2 in the current basis and axes 0, 3 in the basis of the last flush, W (n, n)
  * the rotation accumulated since:  Gamma[a,b,c,d] = sum W[a,a'] W[d,d'] S[a',b,c,d'].  A rank holds the
@@ -184,6 +190,8 @@ int qio_b200_contract_axis(const double *U, const double *in, double *out, int n
  * again: contract_axis(W, S -> work, leading) then contract_axis(W, work -> S, last), then sweep_reset. */
 typedef struct qio_b200_peers {
     int32_t rank, nranks;
+    uint32_t epoch;         /* must differ between consecutive sweep_cycle calls and agree on all ranks */
+    uint32_t reserved;
     void *const *mailboxes; /* DEVICE array [nranks] of mailbox base pointers as mapped into THIS process
                                (own + cudaIpc-opened peers); each mailbox has qio_b200_mailbox_bytes(nranks) */
 } qio_b200_peers;

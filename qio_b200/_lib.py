@@ -41,7 +41,8 @@ class ThetaTables(ctypes.Structure):
 
 class Peers(ctypes.Structure):
     """struct qio_b200_peers"""
-    _fields_ = [('rank', ctypes.c_int32), ('nranks', ctypes.c_int32), ('mailboxes', ctypes.c_void_p)]
+    _fields_ = [('rank', ctypes.c_int32), ('nranks', ctypes.c_int32), ('epoch', ctypes.c_uint32),
+                ('reserved', ctypes.c_uint32), ('mailboxes', ctypes.c_void_p)]
 
 
 if not os.path.exists(LIB_PATH):
@@ -75,6 +76,7 @@ SIGNATURES = {
     'qio_b200_rotate_rdm2': ([_p, _p, _p, _i, _p], _i),
     'qio_b200_rotate_axis': ([_p, _p, _p, _i, _ll, _ll, _p], _i),
     'qio_b200_contract_axis': ([_p, _p, _p, _i, _ll, _i, _p], _i),
+    'qio_b200_contract_axis_partial': ([_p, _ll, _p, _p, _i, _i, _ll, _p], _i),
     'qio_b200_sweep_workspace_bytes': ([_i], ctypes.c_size_t),
     'qio_b200_sweep_reset': ([_p, _i, _p], _i),
     'qio_b200_mailbox_bytes': ([_i], ctypes.c_size_t),

@@ -47,6 +47,7 @@ struct LineSearchSmemT {
     MinIdx best;
     double cost0;
     double margin;
+    double cs_acc[2];                 // cos, sin of the accepted angle
     long long prof[8];                // cycles thread 0 spent per stage (coarse, reduce, fine, scan, margin, tail)
     long long prof_last;
 };
@@ -116,11 +117,12 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
     // ---- fine grid of that coarse point ---------------------------------------------------
     const int L = min(tab.fine_len[row], LS_MAX_FINE);
     const double2 *fcs = reinterpret_cast<const double2 *>(tab.fine_cs) + (size_t)row * tab.fine_stride;
+    double2 my_cs = make_double2(1.0, 0.0);
     if (tid < LS_MAX_FINE) {
         double v = INFINITY;
         if (tid < L) {
-            const double2 cs = fcs[tid];
-            v = pair_cost(b, cs.x, cs.y, i_in, j_in, flags);
+            my_cs = fcs[tid];
+            v = pair_cost(b, my_cs.x, my_cs.y, i_in, j_in, flags);
         }
         sm.fine_val[tid] = v;
         sm.fine_thr[tid] = __dadd_rn(v, 1e-8);      // +inf (or NaN) beyond L: never accepted
@@ -138,6 +140,9 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
     __syncthreads();
     int last = -1;          // last accepted index (uniform over the CTA)
     double cur = start;     // running cost (uniform)
+    unsigned am[LS_MAX_FINE / 32];
+#pragma unroll
+    for (int w = 0; w < LS_MAX_FINE / 32; ++w) am[w] = sm.amask[w];
     for (;;) {
         if (tid < LS_MAX_FINE) {
             const bool pred = tid > last && sm.fine_thr[tid] < cur;     // tid < L implied (thr = +inf beyond)
@@ -149,13 +154,29 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
 #pragma unroll
         for (int w = 0; w < LS_MAX_FINE / 32; ++w) first = min(first, sm.wfirst[w]);
         if (first == 0x7fffffff) break;
-        // extend over the run of consecutive accepts that follows
-        int e = first;
-        while (e + 1 < L && ((sm.amask[(e + 1) >> 5] >> ((e + 1) & 31)) & 1u)) ++e;
+        // extend over the run of consecutive accepts that follows: first zero bit of the mask above `first`
+        // (bits at and beyond L are zero by construction, so the run always ends before L)
+        int e = LS_MAX_FINE - 1;
+        bool found = false;
+#pragma unroll
+        for (int w = 0; w < LS_MAX_FINE / 32; ++w) {
+            const int base = w * 32;
+            unsigned zeros = ~am[w];                                     // candidate run ends (bit k clear)
+            if (first + 1 >= base + 32) zeros = 0;                       // word entirely at or below `first`
+            else if (first + 1 > base) zeros &= ~0u << (first + 1 - base);
+            if (!found && zeros) {
+                e = base + __ffs(zeros) - 2;                             // last set bit before the first zero
+                found = true;
+            }
+        }
         if (tid >= first && tid <= e) sm.accepted[tid] = 1;
         last = e;
         cur = sm.fine_val[e];
         __syncthreads();        // wfirst is rewritten in the next round
+    }
+    if (tid == last) {
+        sm.cs_acc[0] = my_cs.x;
+        sm.cs_acc[1] = my_cs.y;
     }
     LS_PROF(3)
 
@@ -200,11 +221,9 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
     res.coarse_margin = coarse_margin;
     res.fine_margin = sm.margin;
     if (fidx >= 0) {
-        const size_t e = (size_t)row * tab.fine_stride + fidx;
-        res.theta = tab.fine_theta[e];
-        const double2 cs = fcs[fidx];
-        res.cos_theta = cs.x;
-        res.sin_theta = cs.y;
+        res.theta = tab.fine_theta[(size_t)row * tab.fine_stride + fidx];     // for the record only
+        res.cos_theta = sm.cs_acc[0];
+        res.sin_theta = sm.cs_acc[1];
     } else {
         res.theta = __longlong_as_double(0x7ff8000000000000LL);
         res.cos_theta = 1.0;

@@ -55,7 +55,7 @@ __device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, doub
 template <int NT8, bool ALIGNED, int MODE>
 __global__ void __launch_bounds__(RA_THREADS, 1)
     rotate_axis_kernel(const double *__restrict__ U, const double *__restrict__ in, double *__restrict__ out, int n,
-                       long long rows, long long ld_in, long long ld_out) {
+                       int kdim, long long ldu, long long rows, long long ld_in, long long ld_out) {
     constexpr int BN = 16 * NT8;
     constexpr int A_STAGE = (MODE == MODE_LAST) ? RA_BM * RA_BPITCH : RA_BK * RA_APITCH;
     extern __shared__ __align__(16) double smem[];
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(RA_THREADS, 1)
     const int wm = (warp & 3) * 32, wn = (warp >> 2) * (8 * NT8);
     const long long m0 = (long long)blockIdx.x * RA_BM;
     const int n0 = blockIdx.y * BN;
-    const int ktiles = (n + RA_BK - 1) / RA_BK;
+    const int ktiles = (kdim + RA_BK - 1) / RA_BK;      // n = number of outputs (rows of U), kdim = contraction length
 
     auto load_stage = [&](int stage, int kt) {
         const int k0 = kt * RA_BK;
@@ -78,14 +78,14 @@ __global__ void __launch_bounds__(RA_THREADS, 1)
             if (ALIGNED) {
                 for (int e = tid; e < RA_BM * (RA_BK / 2); e += RA_THREADS) {
                     const int mr = e / (RA_BK / 2), kc = (e % (RA_BK / 2)) * 2;
-                    const bool ok = (m0 + mr < rows) && (k0 + kc < n);
+                    const bool ok = (m0 + mr < rows) && (k0 + kc < kdim);
                     const double *src = ok ? in + (m0 + mr) * ld_in + k0 + kc : in;
                     cp_async16(a + mr * RA_BPITCH + kc, src, ok);
                 }
             } else {
                 for (int e = tid; e < RA_BM * RA_BK; e += RA_THREADS) {
                     const int mr = e / RA_BK, kc = e % RA_BK;
-                    const bool ok = (m0 + mr < rows) && (k0 + kc < n);
+                    const bool ok = (m0 + mr < rows) && (k0 + kc < kdim);
                     const double *src = ok ? in + (m0 + mr) * ld_in + k0 + kc : in;
                     cp_async8(a + mr * RA_BPITCH + kc, src, ok);
                 }
@@ -94,14 +94,14 @@ __global__ void __launch_bounds__(RA_THREADS, 1)
             // A tile: 16 rows (k) x 128 contiguous m
             for (int e = tid; e < RA_BK * (RA_BM / 2); e += RA_THREADS) {
                 const int kr = e / (RA_BM / 2), mc = (e % (RA_BM / 2)) * 2;
-                const bool ok = (k0 + kr < n) && (m0 + mc < rows);
+                const bool ok = (k0 + kr < kdim) && (m0 + mc < rows);
                 const double *src = ok ? in + (long long)(k0 + kr) * ld_in + m0 + mc : in;
                 cp_async16(a + kr * RA_APITCH + mc, src, ok);
             }
         } else {
             for (int e = tid; e < RA_BK * RA_BM; e += RA_THREADS) {
                 const int kr = e / RA_BM, mc = e % RA_BM;
-                const bool ok = (k0 + kr < n) && (m0 + mc < rows);
+                const bool ok = (k0 + kr < kdim) && (m0 + mc < rows);
                 const double *src = ok ? in + (long long)(k0 + kr) * ld_in + m0 + mc : in;
                 cp_async8(a + kr * RA_APITCH + mc, src, ok);
             }
@@ -110,15 +110,15 @@ __global__ void __launch_bounds__(RA_THREADS, 1)
         if (ALIGNED) {
             for (int e = tid; e < BN * (RA_BK / 2); e += RA_THREADS) {
                 const int nr = e / (RA_BK / 2), kc = (e % (RA_BK / 2)) * 2;
-                const bool ok = (n0 + nr < n) && (k0 + kc < n);
-                const double *src = ok ? U + (long long)(n0 + nr) * n + k0 + kc : U;
+                const bool ok = (n0 + nr < n) && (k0 + kc < kdim);
+                const double *src = ok ? U + (long long)(n0 + nr) * ldu + k0 + kc : U;
                 cp_async16(b + nr * RA_BPITCH + kc, src, ok);
             }
         } else {
             for (int e = tid; e < BN * RA_BK; e += RA_THREADS) {
                 const int nr = e / RA_BK, kc = e % RA_BK;
-                const bool ok = (n0 + nr < n) && (k0 + kc < n);
-                const double *src = ok ? U + (long long)(n0 + nr) * n + k0 + kc : U;
+                const bool ok = (n0 + nr < n) && (k0 + kc < kdim);
+                const double *src = ok ? U + (long long)(n0 + nr) * ldu + k0 + kc : U;
                 cp_async8(b + nr * RA_BPITCH + kc, src, ok);
             }
         }
@@ -188,28 +188,28 @@ __global__ void __launch_bounds__(RA_THREADS, 1)
 }
 
 template <int NT8, int MODE>
-static int launch_rotate_axis(const double *U, const double *in, double *out, int n, long long rows, long long ld_in,
-                              long long ld_out, cudaStream_t st) {
+static int launch_rotate_axis(const double *U, const double *in, double *out, int n, int kdim, long long ldu,
+                              long long rows, long long ld_in, long long ld_out, cudaStream_t st) {
     constexpr int BN = 16 * NT8;
     constexpr int A_STAGE = (MODE == MODE_LAST) ? RA_BM * RA_BPITCH : RA_BK * RA_APITCH;
     const size_t smem = sizeof(double) * (RA_STAGES * A_STAGE + RA_STAGES * BN * RA_BPITCH);
-    const bool aligned = (n % 2 == 0) && (ld_in % 2 == 0) && (ld_out % 2 == 0) && (rows % 2 == 0) &&
+    const bool aligned = (n % 2 == 0) && (kdim % 2 == 0) && (ldu % 2 == 0) && (ld_in % 2 == 0) && (ld_out % 2 == 0) && (rows % 2 == 0) &&
                          ((uintptr_t)in % 16 == 0) && ((uintptr_t)U % 16 == 0) && ((uintptr_t)out % 16 == 0);
     dim3 grid((unsigned)((rows + RA_BM - 1) / RA_BM), (unsigned)((n + BN - 1) / BN));
     if (aligned) {
         QIO_CUDA(cudaFuncSetAttribute(rotate_axis_kernel<NT8, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rotate_axis_kernel<NT8, true, MODE><<<grid, RA_THREADS, smem, st>>>(U, in, out, n, rows, ld_in, ld_out);
+        rotate_axis_kernel<NT8, true, MODE><<<grid, RA_THREADS, smem, st>>>(U, in, out, n, kdim, ldu, rows, ld_in, ld_out);
     } else {
         QIO_CUDA(cudaFuncSetAttribute(rotate_axis_kernel<NT8, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rotate_axis_kernel<NT8, false, MODE><<<grid, RA_THREADS, smem, st>>>(U, in, out, n, rows, ld_in, ld_out);
+        rotate_axis_kernel<NT8, false, MODE><<<grid, RA_THREADS, smem, st>>>(U, in, out, n, kdim, ldu, rows, ld_in, ld_out);
     }
     QIO_LAUNCH_CHECK();
     return QIO_B200_OK;
 }
 
 template <int MODE>
-static int dispatch_rotate_axis(const double *U, const double *in, double *out, int n, long long rows, long long ld_in,
-                                long long ld_out, cudaStream_t st) {
+static int dispatch_rotate_axis(const double *U, const double *in, double *out, int n, int kdim, long long ldu,
+                                long long rows, long long ld_in, long long ld_out, cudaStream_t st) {
     // N tile = 16*NT8 columns: fewest padded columns, ties to the wider tile
     int best = 1;
     long long best_pad = -1;
@@ -222,13 +222,13 @@ static int dispatch_rotate_axis(const double *U, const double *in, double *out, 
         }
     }
     switch (best) {
-        case 1: return launch_rotate_axis<1, MODE>(U, in, out, n, rows, ld_in, ld_out, st);
-        case 2: return launch_rotate_axis<2, MODE>(U, in, out, n, rows, ld_in, ld_out, st);
-        case 3: return launch_rotate_axis<3, MODE>(U, in, out, n, rows, ld_in, ld_out, st);
-        case 4: return launch_rotate_axis<4, MODE>(U, in, out, n, rows, ld_in, ld_out, st);
-        case 5: return launch_rotate_axis<5, MODE>(U, in, out, n, rows, ld_in, ld_out, st);
-        case 6: return launch_rotate_axis<6, MODE>(U, in, out, n, rows, ld_in, ld_out, st);
-        default: return launch_rotate_axis<7, MODE>(U, in, out, n, rows, ld_in, ld_out, st);
+        case 1: return launch_rotate_axis<1, MODE>(U, in, out, n, kdim, ldu, rows, ld_in, ld_out, st);
+        case 2: return launch_rotate_axis<2, MODE>(U, in, out, n, kdim, ldu, rows, ld_in, ld_out, st);
+        case 3: return launch_rotate_axis<3, MODE>(U, in, out, n, kdim, ldu, rows, ld_in, ld_out, st);
+        case 4: return launch_rotate_axis<4, MODE>(U, in, out, n, kdim, ldu, rows, ld_in, ld_out, st);
+        case 5: return launch_rotate_axis<5, MODE>(U, in, out, n, kdim, ldu, rows, ld_in, ld_out, st);
+        case 6: return launch_rotate_axis<6, MODE>(U, in, out, n, kdim, ldu, rows, ld_in, ld_out, st);
+        default: return launch_rotate_axis<7, MODE>(U, in, out, n, kdim, ldu, rows, ld_in, ld_out, st);
     }
 }
 
@@ -259,7 +259,7 @@ extern "C" int qio_b200_rotate_axis(const double *U, const double *in, double *o
     QIO_REQUIRE(n > 0 && rows >= 0 && ld_in >= rows, "rotate_axis: bad sizes");
     if (rows == 0) return QIO_B200_OK;
     QIO_REQUIRE(U && in && out && in != out, "rotate_axis: bad pointers");
-    return dispatch_rotate_axis<MODE_CYCLIC>(U, in, out, n, rows, ld_in, n, as_stream(stream));
+    return dispatch_rotate_axis<MODE_CYCLIC>(U, in, out, n, n, n, rows, ld_in, n, as_stream(stream));
 }
 
 extern "C" int qio_b200_contract_axis(const double *U, const double *in, double *out, int n, long long rows,
@@ -268,8 +268,21 @@ extern "C" int qio_b200_contract_axis(const double *U, const double *in, double 
     QIO_REQUIRE(n > 0 && rows >= 0, "contract_axis: bad sizes");
     if (rows == 0) return QIO_B200_OK;
     QIO_REQUIRE(U && in && out && in != out, "contract_axis: bad pointers");
-    if (last_axis) return dispatch_rotate_axis<MODE_LAST>(U, in, out, n, rows, n, n, as_stream(stream));
-    return dispatch_rotate_axis<MODE_LEAD_KEEP>(U, in, out, n, rows, rows, rows, as_stream(stream));
+    if (last_axis) return dispatch_rotate_axis<MODE_LAST>(U, in, out, n, n, n, rows, n, n, as_stream(stream));
+    return dispatch_rotate_axis<MODE_LEAD_KEEP>(U, in, out, n, n, n, rows, rows, rows, as_stream(stream));
+}
+
+extern "C" int qio_b200_contract_axis_partial(const double *U, long long ldu, const double *in, double *out, int n,
+                                              int kdim, long long rows, void *stream) {
+    using namespace qio;
+    QIO_REQUIRE(n > 0 && kdim >= 0 && rows >= 0 && ldu >= kdim, "contract_axis_partial: bad sizes");
+    if (rows == 0) return QIO_B200_OK;
+    QIO_REQUIRE(U && out && (in || kdim == 0) && in != out, "contract_axis_partial: bad pointers");
+    if (kdim == 0) {
+        QIO_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)n * rows, as_stream(stream)));
+        return QIO_B200_OK;
+    }
+    return dispatch_rotate_axis<MODE_LEAD_KEEP>(U, in, out, n, kdim, ldu, rows, rows, rows, as_stream(stream));
 }
 
 extern "C" int qio_b200_rotate_rdm2(const double *U, double *Gamma, double *work, int n, void *stream) {

@@ -31,7 +31,7 @@ namespace qio {
 constexpr int SW_THREADS = 512;
 constexpr int SW_WARPS = SW_THREADS / 32;      // 16 = one (q, r) row task per warp
 constexpr int SB_DOUBLES = 256 + 32;           // super block + the 2 x 4 x 4 gamma entries
-constexpr int MB_STRIDE = 256 + 8;             // mailbox slot: 256 doubles + flag (+ padding)
+constexpr int MB_STRIDE = 512;                 // mailbox slot: 256 x (value, tag) 16-byte words, in doubles
 
 struct SweepParams {
     double *S, *gamma, *U, *W;
@@ -46,6 +46,7 @@ struct SweepParams {
     unsigned *bar;             // [0] arrival counter (monotone), [1] generation
     double *summary;           // [16]
     int rank, nranks;
+    unsigned long long epoch;  // distinguishes launches in the mailbox tags
     double *const *mailboxes;  // [nranks] peer-mapped mailbox bases, layout [2][nranks][MB_STRIDE]; NULL if nranks == 1
 };
 
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepParams p) {
     __shared__ double sb[SB_DOUBLES];
     __shared__ PairCoef pc;
     __shared__ double2 coarse_cs_sm[320];
+    __shared__ int32_t fine_len_sm[320];
     extern __shared__ double wrow_sm[];       // [4][n] rows of W for the super-block phase
     const int n = p.n, tid = threadIdx.x;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -313,9 +315,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepParams p) {
 
     if (tid < 8) ls.prof[tid] = 0;
     ThetaTablesDev tab = p.tab;
-    if (cta == 0 && tab.n_coarse <= 320) {      // the search CTA keeps the coarse cos/sin table in shared memory
-        for (int t = tid; t < tab.n_coarse; t += SW_THREADS) coarse_cs_sm[t] = reinterpret_cast<const double2 *>(tab.coarse_cs)[t];
+    if (cta == 0 && tab.n_coarse <= 320) {      // the search CTA keeps the coarse cos/sin table and the fine lengths in smem
+        for (int t = tid; t < tab.n_coarse; t += SW_THREADS) {
+            coarse_cs_sm[t] = reinterpret_cast<const double2 *>(tab.coarse_cs)[t];
+            fine_len_sm[t] = tab.fine_len[t];
+        }
         tab.coarse_cs = reinterpret_cast<const double *>(coarse_cs_sm);
+        tab.fine_len = fine_len_sm;
     }
     // who does the small replicated updates
     const int cta_gamma = G > 1 ? G - 1 : 0, cta_wu = G > 2 ? G - 2 : (G > 1 ? 1 : 0);
@@ -360,35 +366,28 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepParams p) {
             sb[tid] = __ldcg(p.pbuf + (size_t)K * SB_DOUBLES + tid);
         }
         if (p.nranks > 1) {
+            // Every 16-byte word carries (value, tag): one NVLink store per element, no fence, no separate flag --
+            // the receiver spins on the tag of each word it needs (the "LL" idea).  Slots alternate with the step
+            // parity; a slot is rewritten two steps later, after every reader has moved on (see the header comment).
             const int par = t & 1;
-            const unsigned long long tag = (unsigned long long)t + 1;
-            __syncthreads();
-            // post this rank's partial into every rank's mailbox, then the tag
-            for (int e = tid; e < 256 * p.nranks; e += SW_THREADS) {
-                const int dst = e >> 8, k = e & 255;
-                p.mailboxes[dst][((size_t)par * p.nranks + p.rank) * MB_STRIDE + k] = sb[k];
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (tid < p.nranks) {
-                volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(
-                    p.mailboxes[tid] + ((size_t)par * p.nranks + p.rank) * MB_STRIDE + 256);
-                *flag = tag;
-            }
-            // wait for every rank's partial of this step
-            if (tid < p.nranks) {
-                volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(
-                    p.mailboxes[p.rank] + ((size_t)par * p.nranks + tid) * MB_STRIDE + 256);
-                while (*flag != tag) {
-                }
-                __threadfence_system();
-            }
+            const unsigned long long tag = (p.epoch << 32) | (unsigned long long)(t + 1);
             __syncthreads();
             if (tid < 256) {
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(sb[tid]);
+                for (int dst = 0; dst < p.nranks; ++dst) {
+                    unsigned long long *w = reinterpret_cast<unsigned long long *>(
+                        p.mailboxes[dst] + ((size_t)par * p.nranks + p.rank) * MB_STRIDE) + 2 * tid;
+                    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(w), "l"(bits), "l"(tag) : "memory");
+                }
                 double acc = 0.0;
                 for (int r = 0; r < p.nranks; ++r) {
-                    const volatile double *slot = p.mailboxes[p.rank] + ((size_t)par * p.nranks + r) * MB_STRIDE;
-                    acc += slot[tid];
+                    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(
+                        p.mailboxes[p.rank] + ((size_t)par * p.nranks + r) * MB_STRIDE) + 2 * tid;
+                    unsigned long long v, g;
+                    do {
+                        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(g) : "l"(w) : "memory");
+                    } while (g != tag);
+                    acc += __longlong_as_double((long long)v);
                 }
                 sb[tid] = acc;
             }
@@ -600,6 +599,7 @@ extern "C" int qio_b200_sweep_cycle(double *gamma, double *S, double *U, double 
     p.summary = summary;
     p.rank = h_peers ? h_peers->rank : 0;
     p.nranks = nranks;
+    p.epoch = h_peers ? (unsigned long long)h_peers->epoch : 0ull;
     p.mailboxes = nranks > 1 ? reinterpret_cast<double *const *>(h_peers->mailboxes) : nullptr;
     int blocks_per_sm = 0;
     QIO_REQUIRE(n <= 4096, "sweep_cycle: n too large for the shared-memory W rows");

@@ -201,6 +201,13 @@ def contract_axis(U, src, dst, n, rows, last_axis):
     return dst
 
 
+def contract_axis_partial(U, ldu, src, dst, n, kdim, rows):
+    """dst[i, m] = sum_{k<kdim} U[i*ldu + k] src[k, m] (U may be a column block of a larger matrix)."""
+    check(lib.qio_b200_contract_axis_partial(_ptr(U), int(ldu), _ptr(src), _ptr(dst), n, int(kdim), int(rows), _stream()),
+          'contract_axis_partial')
+    return dst
+
+
 def sweep_reset(W, n):
     check(lib.qio_b200_sweep_reset(_ptr(W), n, _stream()), 'sweep_reset')
 
@@ -213,6 +220,8 @@ def sweep_cycle(gamma, S, U, W, n, pairs, mask, tables, a0=0, na=None, peers=Non
     results = torch.empty(max(P, 1) * LS_DTYPE.itemsize, dtype=torch.uint8, device=require_cuda())
     summary = empty(16)
     ws = torch.empty(int(lib.qio_b200_sweep_workspace_bytes(n)), dtype=torch.uint8, device=require_cuda())
+    if peers is not None:
+        peers.next_epoch()
     check(lib.qio_b200_sweep_cycle(_ptr(gamma), _ptr(S), _ptr(U), _ptr(W), n, a0, na, _ptr(pairs), P, _ptr(mask),
                                     ctypes.byref(tables.struct), _ptr(results), _ptr(summary), _ptr(ws),
                                     ctypes.byref(peers.struct) if peers is not None else None, _stream()),
