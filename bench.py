@@ -211,6 +211,8 @@ def run_reference_arm(args):
 # B200 arm
 # --------------------------------------------------------------------------------------------------
 def run_b200_arm(args):
+    if not os.environ.get('QIO_BENCH_KEEP_NCCL_DEBUG'):
+        os.environ['NCCL_DEBUG'] = 'WARN'       # keep NCCL's version banner off stdout: rank 0 prints one JSON line only
     import torch
     import torch.distributed as dist
 
@@ -364,10 +366,10 @@ def run_b200_arm(args):
     sweep_ms = timed(lambda: dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs), 1)
     phases['jacobi_cycle_kernel_first_cycle_ms'] = sweep_ms
     tsum = dev.to_host(dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs)[1])
-    names = ['prologue', 'search_cta0', 'cta0_idle_tail', 'barrier1', 'superblock_and_barrier2', 'gather']
-    phases['sweep_phase_us_per_pair_cta0'] = {k: float(v) / 1e3 / len(pairs_np) for k, v in zip(names, tsum[4:10])}
+    phases['sweep_phase_us_per_pair'] = sweep_phase_table(tsum, len(pairs_np))
     lsn = ['coarse', 'reduce', 'fine', 'scan', 'margin', 'tail']
     phases['linesearch_cycles_per_pair_cta0'] = {k: float(v) / len(pairs_np) for k, v in zip(lsn, tsum[10:16])}
+    phases['linesearch_cycles_per_pair_cta0'].update(block_setup=float(tsum[20]) / len(pairs_np), result_store=float(tsum[21]) / len(pairs_np))
     algo_bytes = 16.0 * (n ** 4 - (n - 2) ** 4) * n_accepted      # bytes the reference update touches
     kernel_bytes = 64.0 * n ** 3 * n_accepted + 32.0 * n * n * len(pairs_np)   # what the deferred layout moves
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
@@ -417,6 +419,15 @@ def run_b200_arm(args):
         'phases': phases,
     }
     print(json.dumps(out))
+
+
+def sweep_phase_table(tsum, npairs):
+    """Per-pair averages (us) of the phase timers the sweep kernel keeps on CTA 0 (search side) and CTA 1 (update side)."""
+    us = lambda v: float(v) / 1e3 / max(npairs, 1)
+    return {'cta0_gather': us(tsum[5]), 'cta0_search': us(tsum[6]), 'cta0_tail': us(tsum[7]), 'cta0_barrier_wait': us(tsum[8]),
+            'cta1_superblock_orbits': us(tsum[16]), 'cta1_flat_update': us(tsum[17]), 'cta1_barrier_wait': us(tsum[18]),
+            'flatcta_update': us(tsum[22]), 'flatcta_barrier_wait': us(tsum[23]),
+            'prologue_total_us': float(tsum[4]) / 1e3}
 
 
 def run_b200_multi(args, rank, world, local_rank):
@@ -532,7 +543,6 @@ def run_b200_multi(args, rank, world, local_rank):
     peak = json.load(open(peaks_path))['hbm_gbs'] if os.path.exists(peaks_path) else 6650.0
     algo_bytes = 16.0 * (n ** 4 - (n - 2) ** 4) * n_acc / world
     achieved = algo_bytes / (sweep_ms * 1e-3) / 1e9
-    names = ['prologue', 'search_cta0', 'cta0_idle_tail', 'barrier1', 'superblock_and_barrier2', 'gather']
     roofline = {'kernel': 'sweep_kernel (persistent Jacobi cycle), per GPU', 'bound': 'hbm', 'achieved': achieved,
                 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                 'algorithmic_bytes_per_launch': algo_bytes, 'avg_launch_ms': sweep_ms, 'launches_timed': 1,
@@ -549,7 +559,7 @@ def run_b200_multi(args, rank, world, local_rank):
             'roofline': roofline, 'cpu_baseline': None, 'evals_per_step': evals_per_step,
             'rotations_accepted': n_acc, 'cost_after_cycle': state['cost'],
             'phases': {'jacobi_cycle_kernel_ms': sweep_ms,
-                       'sweep_phase_us_per_pair_cta0': {k: float(v) / 1e3 / len(pairs_np) for k, v in zip(names, tsum[4:10])}},
+                       'sweep_phase_us_per_pair': sweep_phase_table(tsum, len(pairs_np))},
         }
         print(json.dumps(out))
     peers.close()

@@ -6,9 +6,11 @@
 //           strictly below cost(0); otherwise t_opt falls back to 0.01 == coarse point 0;
 //   fine:   accept k iff cost > cost_k + 1e-8, then cost = cost_k.  The chain is sequential in
 //           principle, but it decomposes into "find the first k beyond the last accepted one with
-//           cost_k + 1e-8 < cost" (a CTA-wide ballot) followed by a run of consecutive accepts
+//           cost_k + 1e-8 < cost" (a ballot over 256 threads) followed by a run of consecutive accepts
 //           (a_k := cost_{k-1} > cost_k + 1e-8, precomputed as a bit mask).  A smooth cost curve needs
 //           two rounds; any other sequence just takes more rounds with the same result.
+// The NT participating threads (the first NT of the CTA) synchronise on a NAMED barrier, so a CTA may
+// have more threads that do something else (or wait elsewhere) meanwhile.
 #pragma once
 #include "pair_math.cuh"
 
@@ -16,6 +18,7 @@ namespace qio {
 
 constexpr int LS_THREADS = 320;           // >= 314 coarse points + 1, 10 warps
 constexpr int LS_MAX_FINE = 256;          // capacity of the fine-value buffers (8 warps x 32)
+constexpr int LS_BARRIER = 1;             // named barrier id used by the line search
 
 struct ThetaTablesDev {                   // device copy of qio_b200_theta_tables (pointers are device pointers)
     int n_coarse, fine_stride;
@@ -40,14 +43,15 @@ template <int NT>
 struct LineSearchSmemT {
     double fine_val[LS_MAX_FINE];     // cost at each fine angle
     double fine_thr[LS_MAX_FINE];     // cost + 1e-8 (rounded add, as the reference's `new_cost + 1e-8`)
-    unsigned char accepted[LS_MAX_FINE];
     unsigned amask[LS_MAX_FINE / 32]; // bit k: cost_{k-1} > cost_k + 1e-8
+    unsigned accmask[LS_MAX_FINE / 32];   // bit k: entry k was accepted by the scan
     int wfirst[LS_MAX_FINE / 32];
+    double wmargin[LS_MAX_FINE / 32];
     MinIdx warp_best[NT / 32];
     MinIdx best;
     double cost0;
-    double margin;
     double cs_acc[2];                 // cos, sin of the accepted angle
+    int flags;
     long long prof[8];                // cycles thread 0 spent per stage (coarse, reduce, fine, scan, margin, tail)
     long long prof_last;
 };
@@ -60,22 +64,31 @@ using LineSearchSmem = LineSearchSmemT<LS_THREADS>;
         sm.prof_last = now_;                        \
     }
 
+template <int NT>
+__device__ __forceinline__ void ls_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(LS_BARRIER), "n"(NT) : "memory");
+}
+
 __device__ __forceinline__ double warp_min_double(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
     return v;
 }
 
-// All NT threads of the CTA (NT >= LS_MAX_FINE) must call this with the same arguments.  The result is
-// returned in every thread (res is filled identically).  `b` is either a PairBlock / PairBlockRef
-// (reference operation order) or a PairCoef (fast polynomial form): pair_cost() is overloaded.
+// Threads 0..NT-1 of the CTA (whole warps, NT >= 256) must call this with the same arguments; the others must not.
+// The result is returned in every participating thread.  `b` is either a PairBlock / PairBlockRef (reference operation
+// order) or a PairCoef (fast polynomial form): pair_cost() is overloaded.
 template <int NT, typename Block>
 __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool j_in, const ThetaTablesDev &tab,
                                                  LineSearchSmemT<NT> &sm, qio_b200_ls_result &res) {
     static_assert(NT >= LS_MAX_FINE && NT % 32 == 0, "line search needs at least 256 threads");
+    constexpr int NW = LS_MAX_FINE / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int flags = 0;
-    if (tid == 0) sm.prof_last = clock64();
+    if (tid == 0) {
+        sm.prof_last = clock64();
+        sm.flags = 0;
+    }
 
     // ---- coarse grid; candidate index n_coarse is theta = 0 (cos = 1, sin = 0 exactly as np.cos(0)) ----
     MinIdx mine;
@@ -99,14 +112,9 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
     LS_PROF(0)
     mine = warp_min(mine);
     if (lane == 0) sm.warp_best[warp] = mine;
-    __syncthreads();
-    if (warp == 0) {
-        MinIdx x = (lane < NT / 32) ? sm.warp_best[lane] : MinIdx{INFINITY, 0x7fffffff, INFINITY};
-        x = warp_min(x);
-        if (lane == 0) sm.best = x;
-    }
-    __syncthreads();
-    const MinIdx best = sm.best;
+    ls_sync<NT>();
+    MinIdx best = (lane < NT / 32) ? sm.warp_best[lane] : MinIdx{INFINITY, 0x7fffffff, INFINITY};
+    best = warp_min(best);              // every warp reduces the NT/32 partial results redundantly: no second barrier
     const double cost0 = sm.cost0;
     const bool improved = cost0 > best.v;
     const int row = improved ? best.idx : 0;
@@ -118,48 +126,53 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
     const int L = min(tab.fine_len[row], LS_MAX_FINE);
     const double2 *fcs = reinterpret_cast<const double2 *>(tab.fine_cs) + (size_t)row * tab.fine_stride;
     double2 my_cs = make_double2(1.0, 0.0);
+    double my_thr = INFINITY;
     if (tid < LS_MAX_FINE) {
         double v = INFINITY;
         if (tid < L) {
             my_cs = fcs[tid];
             v = pair_cost(b, my_cs.x, my_cs.y, i_in, j_in, flags);
         }
+        my_thr = __dadd_rn(v, 1e-8);                // +inf (or NaN) beyond L: never accepted
         sm.fine_val[tid] = v;
-        sm.fine_thr[tid] = __dadd_rn(v, 1e-8);      // +inf (or NaN) beyond L: never accepted
-        sm.accepted[tid] = 0;
+        sm.fine_thr[tid] = my_thr;
     }
-    const int any_flags = __syncthreads_or(flags);
+    if (flags) atomicOr(&sm.flags, flags);
+    ls_sync<NT>();
     LS_PROF(2)
 
-    // ---- the accept scan -----------------------------------------------------------------------
+    // ---- the accept scan (warps 0..7 hold one fine entry per thread) -------------------------------
     if (tid < LS_MAX_FINE) {
-        const bool a = tid > 0 && tid < L && sm.fine_val[tid - 1] > sm.fine_thr[tid];
+        const bool a = tid > 0 && tid < L && sm.fine_val[tid - 1] > my_thr;
         const unsigned m = __ballot_sync(0xffffffffu, a);
-        if (lane == 0) sm.amask[warp] = m;
+        if (lane == 0) {
+            sm.amask[warp] = m;
+            sm.accmask[warp] = 0;
+        }
     }
-    __syncthreads();
-    int last = -1;          // last accepted index (uniform over the CTA)
+    ls_sync<NT>();
+    int last = -1;          // last accepted index (uniform over the participants)
     double cur = start;     // running cost (uniform)
-    unsigned am[LS_MAX_FINE / 32];
+    unsigned am[NW];
 #pragma unroll
-    for (int w = 0; w < LS_MAX_FINE / 32; ++w) am[w] = sm.amask[w];
+    for (int w = 0; w < NW; ++w) am[w] = sm.amask[w];
     for (;;) {
         if (tid < LS_MAX_FINE) {
-            const bool pred = tid > last && sm.fine_thr[tid] < cur;     // tid < L implied (thr = +inf beyond)
+            const bool pred = tid > last && my_thr < cur;       // tid < L implied (thr = +inf beyond)
             const unsigned m = __ballot_sync(0xffffffffu, pred);
             if (lane == 0) sm.wfirst[warp] = m ? (warp * 32 + __ffs(m) - 1) : 0x7fffffff;
         }
-        __syncthreads();
+        ls_sync<NT>();
         int first = 0x7fffffff;
 #pragma unroll
-        for (int w = 0; w < LS_MAX_FINE / 32; ++w) first = min(first, sm.wfirst[w]);
+        for (int w = 0; w < NW; ++w) first = min(first, sm.wfirst[w]);
         if (first == 0x7fffffff) break;
         // extend over the run of consecutive accepts that follows: first zero bit of the mask above `first`
         // (bits at and beyond L are zero by construction, so the run always ends before L)
         int e = LS_MAX_FINE - 1;
         bool found = false;
 #pragma unroll
-        for (int w = 0; w < LS_MAX_FINE / 32; ++w) {
+        for (int w = 0; w < NW; ++w) {
             const int base = w * 32;
             unsigned zeros = ~am[w];                                     // candidate run ends (bit k clear)
             if (first + 1 >= base + 32) zeros = 0;                       // word entirely at or below `first`
@@ -169,10 +182,13 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
                 found = true;
             }
         }
-        if (tid >= first && tid <= e) sm.accepted[tid] = 1;
+        if (tid < LS_MAX_FINE && lane == 0) {                            // record the accepted run [first, e]
+            const int lo = max(first, warp * 32), hi = min(e, warp * 32 + 31);
+            if (lo <= hi) sm.accmask[warp] |= (hi - lo == 31 ? ~0u : ((1u << (hi - lo + 1)) - 1u) << (lo - warp * 32));
+        }
         last = e;
         cur = sm.fine_val[e];
-        __syncthreads();        // wfirst is rewritten in the next round
+        ls_sync<NT>();        // wfirst is rewritten in the next round
     }
     if (tid == last) {
         sm.cs_acc[0] = my_cs.x;
@@ -180,46 +196,40 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
     }
     LS_PROF(3)
 
-    // ---- smallest |cost - (new_cost + 1e-8)| over every comparison of the reference's scan (warp 0) -------
-    __syncthreads();
-    if (warp == 0) {
-        constexpr int PER = LS_MAX_FINE / 32;
-        int chunk_last = -1;
+    // ---- smallest |cost - (new_cost + 1e-8)| over every comparison of the reference's scan ---------------
+    // entry k was compared against the cost of the last accepted entry before k (or the starting cost)
+    ls_sync<NT>();
+    if (tid < LS_MAX_FINE) {
+        unsigned accw[NW];
 #pragma unroll
-        for (int e = 0; e < PER; ++e)
-            if (sm.accepted[lane * PER + e]) chunk_last = lane * PER + e;
-        int incl = chunk_last;
+        for (int w = 0; w < NW; ++w) accw[w] = sm.accmask[w];
+        int prev = -1;
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl = max(incl, t);
+        for (int w = 0; w < NW; ++w) {
+            unsigned m = accw[w];
+            if (w > warp) m = 0;
+            else if (w == warp) m &= (lane == 0) ? 0u : (~0u >> (32 - lane));     // bits below this thread's entry
+            if (m) prev = w * 32 + 31 - __clz(m);
         }
-        int prev = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) prev = -1;
         double mg = INFINITY;
-#pragma unroll
-        for (int e = 0; e < PER; ++e) {
-            const int k = lane * PER + e;
-            if (k < L) {
-                const double cb = prev >= 0 ? sm.fine_val[prev] : start;
-                mg = fmin(mg, fabs(cb - sm.fine_thr[k]));
-                if (sm.accepted[k]) prev = k;
-            }
-        }
+        if (tid < L) mg = fabs((prev >= 0 ? sm.fine_val[prev] : start) - my_thr);
         mg = warp_min_double(mg);
-        if (lane == 0) sm.margin = mg;
+        if (lane == 0) sm.wmargin[warp] = mg;
     }
-    __syncthreads();
+    ls_sync<NT>();
+    double margin = INFINITY;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) margin = fmin(margin, sm.wmargin[w]);
     LS_PROF(4)
     const int fidx = last;
     res.coarse_index = improved ? best.idx : -1;
     res.fine_index = fidx;
-    res.flags = any_flags & (QIO_B200_FLAG_WARN_NEGATIVE | QIO_B200_FLAG_RAISE_GT1);
+    res.flags = sm.flags & (QIO_B200_FLAG_WARN_NEGATIVE | QIO_B200_FLAG_RAISE_GT1);
     res.accepted = fidx >= 0 ? 1 : 0;
     res.cost = cur;
     res.cost0 = cost0;
     res.coarse_margin = coarse_margin;
-    res.fine_margin = sm.margin;
+    res.fine_margin = margin;
     if (fidx >= 0) {
         res.theta = tab.fine_theta[(size_t)row * tab.fine_stride + fidx];     // for the record only
         res.cos_theta = sm.cs_acc[0];
@@ -231,7 +241,7 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
     }
     res.reserved = 0.0;
     LS_PROF(5)
-    __syncthreads();   // smem may be reused by the caller
+    ls_sync<NT>();   // smem may be reused by the caller
 }
 
 __device__ __forceinline__ void cta_linesearch(const PairBlock &b, bool i_in, bool j_in, const ThetaTablesDev &tab,

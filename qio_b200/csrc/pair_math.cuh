@@ -107,6 +107,7 @@ struct PairCoef {
     double A[5];
     double gu[3];   // g_ii, g_ij + g_ji, g_jj  (up)
     double gd[3];   // (down)
+    int sym;        // up and down blocks are bitwise equal (singlet): nu == nd, two spectrum entries coincide
 };
 
 __device__ __forceinline__ void make_coef(const double *rec /* 24-double block */, PairCoef &pc) {
@@ -121,6 +122,7 @@ __device__ __forceinline__ void make_coef(const double *rec /* 24-double block *
     pc.gd[0] = rec[20];
     pc.gd[1] = rec[21] + rec[22];
     pc.gd[2] = rec[23];
+    pc.sym = (pc.gu[0] == pc.gd[0] && pc.gu[1] == pc.gd[1] && pc.gu[2] == pc.gd[2]) ? 1 : 0;
 }
 
 // ln(x) for positive normal x, fdlibm's algorithm (error < 1 ulp; 1 ulp max against glibc on 2e7 samples),
@@ -217,11 +219,39 @@ __device__ __forceinline__ double masked_entropy4_fast(double s0, double s1, dou
 
 // Deliberately NOT inlined: the line search calls it from three places and the persistent sweep kernel is
 // instruction-fetch bound when the loop body outgrows the instruction cache.
+// Spin-symmetric case: the spectrum is [s0, s1, s1, s3]; three logarithms, the same sum ((t0 + t1) + t1) + t3.
+__device__ __forceinline__ double masked_entropy3_sym(double s0, double s1, double s3, int &flags) {
+    const double sp[3] = {s0, s1, s3};
+    double arg[3], lg[3];
+    bool any_neg = false, big_neg = false, gt1 = false;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double p = sp[r];
+        any_neg |= (p < 0.0);
+        big_neg |= (p < -1e-6);
+        gt1 |= (p > 1.0);
+        arg[r] = fmax(p, 1e-300);
+    }
+    log_pos_n<3>(arg, lg);
+    double term[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) term[r] = (sp[r] > 1e-300) ? sp[r] * lg[r] : 0.0;
+    flags |= any_neg ? (big_neg ? QIO_B200_FLAG_WARN_NEGATIVE : 0) : (gt1 ? QIO_B200_FLAG_RAISE_GT1 : 0);
+    return -(((term[0] + term[1]) + term[1]) + term[2]);
+}
+
 static __device__ __noinline__ double pair_cost(const PairCoef &pc, double c, double s, bool i_in, bool j_in, int &flags) {
     const double c2 = c * c, s2 = s * s, cs = c * s, c2s2 = c2 * s2;
     const double nn_i = c2 * (pc.A[0] * c2 + pc.A[1] * cs) + pc.A[2] * c2s2 + s2 * (pc.A[3] * cs + pc.A[4] * s2);
     const double nn_j = s2 * (pc.A[0] * s2 - pc.A[1] * cs) + pc.A[2] * c2s2 + c2 * (pc.A[4] * c2 - pc.A[3] * cs);
     const double nu_i = pc.gu[0] * c2 + pc.gu[1] * cs + pc.gu[2] * s2, nu_j = pc.gu[0] * s2 - pc.gu[1] * cs + pc.gu[2] * c2;
+    if (pc.sym) {       // nd == nu bit for bit
+        int fi = 0, fj = 0;
+        const double Si = masked_entropy3_sym(1.0 - nu_i - nu_i + nn_i, nu_i - nn_i, nn_i, fi);
+        const double Sj = masked_entropy3_sym(1.0 - nu_j - nu_j + nn_j, nu_j - nn_j, nn_j, fj);
+        flags |= (i_in ? fi : 0) | (j_in ? fj : 0);
+        return (i_in ? Si : 0.0) + (j_in ? Sj : 0.0);
+    }
     const double nd_i = pc.gd[0] * c2 + pc.gd[1] * cs + pc.gd[2] * s2, nd_j = pc.gd[0] * s2 - pc.gd[1] * cs + pc.gd[2] * c2;
     int fi = 0, fj = 0;
     const double Si = masked_entropy4_fast(1.0 - nu_i - nd_i + nn_i, nu_i - nn_i, nd_i - nn_i, nn_i, fi);

@@ -16,11 +16,14 @@
 // the "super block" over the <= 4 orbitals D = {i_t, j_t, i_t+1, j_t+1} taken BEFORE rotation t:
 //     SB[p,q,r,s] = sum_{a'} W[D_p,a'] ( S[a',D_q,D_r,:] . W[D_s,:] )        (<= 256 numbers)
 //     B_{t+1} = T^(x4) SB,  T = 2 x |D| coefficients of (i_t+1, j_t+1) after the rotation (cos, sin of pair t).
-// So as soon as theta_t is known, CTA 0 can search pair t+1 while all other CTAs stream the update of pair t:
-//   loop t:   [ CTA 0: B_{t+1} <- SB_t, theta_t; line search t+1 ]  ||  [ CTAs 1..: Givens update t on S, gamma, W, U ]
+// So as soon as theta_t is known, CTA 0 can search pair t+1 while all other CTAs stream the update of pair t, and the
+// super block needed for pair t+2 is produced INSIDE that update: the few d-rows (a', x, y, :) with x, y in D_{t+1} are
+// owned by dedicated warps which load the orbit of such a row under rotation t (1, 2 or 4 rows), rotate it in registers,
+// write it back and take the dot products of the NEW values with the NEW rows of W on the fly.  One grid barrier per pair:
+//   loop t:   [ CTA 0: gather SB_t partials (ranks: peer mailboxes); B_{t+1} <- SB_t, theta_t; line search t+1 ]
+//          || [ CTAs 1..: super-block orbits of SB_{t+1} (update + dots), flat Givens update of everything else,
+//                         gamma, W (ping-pong buffers), U ]
 //             -- grid barrier --
-//             all CTAs: partial SB_{t+1} from the updated state (|D|^2 n rows, |D| dot products each)
-//             -- grid barrier --   CTA 0 sums the partials in a fixed order (and across ranks through peer mailboxes)
 // The flush (W applied to axes 0 and 3 with two DMMA GEMM passes) happens once, when the caller wants Gamma back.
 #include <string.h>
 
@@ -41,10 +44,12 @@ struct SweepParams {
     const int32_t *inactive;
     ThetaTablesDev tab;
     qio_b200_ls_result *results;
-    double *pbuf;              // [K + 1][SB_DOUBLES]
+    double *W2;                // second W buffer (ping-pong), n x n, in the workspace
+    double *dbg;               // [2 * WS_MAX_CTAS] per-CTA arrival / release times of one mid-sweep barrier (ns)
+    double *pbuf;              // [2][nsb + 1][SB_DOUBLES] (parity of the step that reads it)
     qio_b200_ls_result *cur;   // [2] published result of the pair being applied (parity of the step)
     unsigned *bar;             // [0] arrival counter (monotone), [1] generation
-    double *summary;           // [16]
+    double *summary;           // [32]
     int rank, nranks;
     unsigned long long epoch;  // distinguishes launches in the mailbox tags
     double *const *mailboxes;  // [nranks] peer-mapped mailbox bases, layout [2][nranks][MB_STRIDE]; NULL if nranks == 1
@@ -56,21 +61,20 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     return v;
 }
 
-// Monotone-counter grid barrier (all CTAs co-resident: cooperative launch).
+// Monotone-counter grid barrier (all CTAs co-resident: cooperative launch).  The arrival is an acq_rel atomic and
+// the generation is published / polled with release / acquire accesses, so no separate fences are needed.
 __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks, unsigned &epoch) {
     __syncthreads();
     if (threadIdx.x == 0) {
         ++epoch;
-        __threadfence();
-        const unsigned prev = atomicAdd(bar, 1u);
+        unsigned prev;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
         if (prev == nblocks * epoch - 1) {
-            __threadfence();
-            atomicExch(bar + 1, epoch);
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(epoch) : "memory");
         } else {
             while (ld_acquire_u32(bar + 1) < epoch) {
             }
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -134,24 +138,26 @@ struct Counter3 {
 // that consecutive threads touch consecutive words.
 template <int V>
 __device__ __forceinline__ void update_S(double *__restrict__ S, int n, int na, int i, int j, double c, double s,
-                                         long long gtid, long long gthreads) {
+                                         long long gtid, long long gthreads, int4 skip, bool skip_orbit4) {
     const long long n1 = n, n2 = n1 * n1, n3 = n2 * n1;
     const int rowv = n / V;          // vector elements per d-row
     // axis 1: rows (a', {i,j}, cc, :) for all (a', cc), cc in {i, j} excluded (they belong to the 4-orbit)
+    // (`skip` lists up to four row indices whose orbits are owned by the super-block warps, -1 = none)
     for (Counter3 k(gtid, gthreads, n, rowv); k.a < na; k.step()) {
-        if (k.r == i || k.r == j) continue;
+        if (k.r == i || k.r == j || k.r == skip.x || k.r == skip.y || k.r == skip.z || k.r == skip.w) continue;
         double *px = S + k.a * n3 + (long long)i * n2 + k.r * n1 + (long long)k.v * V;
         double *py = S + k.a * n3 + (long long)j * n2 + k.r * n1 + (long long)k.v * V;
         if (V == 2) butterfly2(px, py, c, s); else butterfly1(px, py, c, s);
     }
     // axis 2: rows (a', b, {i,j}, :) for all (a', b), b in {i, j} excluded
     for (Counter3 k(gtid, gthreads, n, rowv); k.a < na; k.step()) {
-        if (k.r == i || k.r == j) continue;
+        if (k.r == i || k.r == j || k.r == skip.x || k.r == skip.y || k.r == skip.z || k.r == skip.w) continue;
         double *px = S + k.a * n3 + k.r * n2 + (long long)i * n1 + (long long)k.v * V;
         double *py = S + k.a * n3 + k.r * n2 + (long long)j * n1 + (long long)k.v * V;
         if (V == 2) butterfly2(px, py, c, s); else butterfly1(px, py, c, s);
     }
     // the 4-row orbit (a', {i,j}, {i,j}, :): both axes
+    if (skip_orbit4) return;
     for (Counter3 k(gtid, gthreads, 1, n); k.a < na; k.step()) {
         double *base = S + k.a * n3 + k.v;
         double *pii = base + (long long)i * n2 + (long long)i * n1, *pij = base + (long long)i * n2 + (long long)j * n1;
@@ -196,53 +202,133 @@ __device__ __forceinline__ Distinct make_distinct(int i, int j, int i2, int j2) 
     return d;
 }
 
-// Partial super block over this CTA's leading-axis slabs -> out[256] (entry ((p*4+q)*4+r)*4+s, 0 if unused).
-// The <= 4 rows of W live in shared memory for the phase; each warp owns one (q, r) row position and walks the
-// CTA's slabs two at a time so that the row loads of both are in flight together.
-__device__ __forceinline__ void superblock_partial(const SweepParams &p, const Distinct &dd, int cta, int apc,
-                                                   double *wrow /* smem [4][n] */, double *out) {
-    const int n = p.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long n1 = n, n2 = n1 * n1, n3 = n2 * n1;
-    for (int e = threadIdx.x; e < dd.nd * n; e += SW_THREADS) {
-        const int s = e / n, d = e - s * n;
-        wrow[e] = __ldcg(p.W + (size_t)dd.D[s] * n + d);
-    }
-    __syncthreads();
-    const int q = warp >> 2, r = warp & 3;
-    const int pl = (lane >> 2) & 3, sl = lane & 3;          // lanes 0..15 own (p, s)
-    double acc = 0.0;
-    if (q < dd.nd && r < dd.nd) {
-        const int first = cta * apc, last = min(first + apc, p.na);
-        for (int al = first; al < last; al += 2) {
-            const bool two = al + 1 < last;
-            const double *row0 = p.S + al * n3 + dd.D[q] * n2 + dd.D[r] * n1;
-            const double *row1 = two ? row0 + n3 : row0;
-            double d0[4] = {0.0, 0.0, 0.0, 0.0}, d1[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int d = lane; d < n; d += 32) {
-                const double v0 = __ldcg(row0 + d), v1 = __ldcg(row1 + d);
-#pragma unroll
-                for (int s = 0; s < 4; ++s)
-                    if (s < dd.nd) {
-                        const double w = wrow[s * n + d];
-                        d0[s] += v0 * w;
-                        d1[s] += v1 * w;
-                    }
-            }
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                d0[s] = warp_sum(d0[s]);
-                d1[s] = warp_sum(d1[s]);
-            }
-            if (lane < 16 && pl < dd.nd && sl < dd.nd) {
-                const double e0 = sl == 0 ? d0[0] : sl == 1 ? d0[1] : sl == 2 ? d0[2] : d0[3];
-                const double e1 = sl == 0 ? d1[0] : sl == 1 ? d1[1] : sl == 2 ? d1[2] : d1[3];
-                acc += wrow[pl * n + p.a0 + al] * e0;
-                if (two) acc += wrow[pl * n + p.a0 + al + 1] * e1;
-            }
+// ---- super-block orbits -------------------------------------------------------------------------------------
+// One task = one orbit of d-rows (b, c) under the rotation being applied (1, 2 or 4 rows) that contains at least one
+// row of the next super block, for one leading-axis slab.
+struct SbTask {
+    int nrows;          // 1, 2 or 4
+    int kind;           // 0 single row, 1 axis-1 pair ((i,f),(j,f)), 2 axis-2 pair ((f,i),(f,j)), 3 the (i,j)x(i,j) orbit
+    int x[4], y[4];     // (b, c) of the rows
+    int nmem;           // rows of this orbit that belong to the super block (<= 4)
+    int mslot[4], mq[4], mr[4];     // their slot in the orbit and their (q, r) position in the super block
+};
+constexpr int SB_MAX_TASKS = 16;
+
+struct SbPlan {
+    SbTask task[SB_MAX_TASKS];
+    int ntasks;
+    int4 skip;          // rows the flat update must leave to the tasks
+    int skip_orbit4;
+};
+
+// Thread 0 of a CTA: orbits of the super block over dd (orbitals of pairs t+1, t+2) under rotation (i, j).
+__device__ __forceinline__ void build_sb_plan(SbPlan &pl, const Distinct &dd, int i, int j, bool rotated) {
+    int cls[4], nE = 0, F[4], Fq[4], nF = 0;
+    for (int q = 0; q < dd.nd; ++q) {
+        cls[q] = rotated ? (dd.D[q] == i ? 1 : dd.D[q] == j ? 2 : 0) : 0;
+        if (cls[q]) ++nE;
+        else {
+            F[nF] = dd.D[q];
+            Fq[nF++] = q;
         }
     }
-    if (lane < 16) out[((pl * 4 + q) * 4 + r) * 4 + sl] = acc;
-    __syncthreads();
+    int nt = 0;
+    for (int a = 0; a < nF; ++a)
+        for (int b = 0; b < nF; ++b) {
+            SbTask &t = pl.task[nt++];
+            t.nrows = 1; t.kind = 0; t.x[0] = F[a]; t.y[0] = F[b];
+            t.nmem = 1; t.mslot[0] = 0; t.mq[0] = Fq[a]; t.mr[0] = Fq[b];
+        }
+    pl.skip = make_int4(-1, -1, -1, -1);
+    pl.skip_orbit4 = 0;
+    if (nE > 0) {
+        for (int a = 0; a < nF; ++a) {
+            {   // rows (i, f), (j, f): rotation of axis 1
+                SbTask &t = pl.task[nt++];
+                t.nrows = 2; t.kind = 1; t.x[0] = i; t.y[0] = F[a]; t.x[1] = j; t.y[1] = F[a]; t.nmem = 0;
+                for (int q = 0; q < dd.nd; ++q)
+                    if (cls[q]) { t.mslot[t.nmem] = cls[q] - 1; t.mq[t.nmem] = q; t.mr[t.nmem] = Fq[a]; ++t.nmem; }
+            }
+            {   // rows (f, i), (f, j): rotation of axis 2
+                SbTask &t = pl.task[nt++];
+                t.nrows = 2; t.kind = 2; t.x[0] = F[a]; t.y[0] = i; t.x[1] = F[a]; t.y[1] = j; t.nmem = 0;
+                for (int r = 0; r < dd.nd; ++r)
+                    if (cls[r]) { t.mslot[t.nmem] = cls[r] - 1; t.mq[t.nmem] = Fq[a]; t.mr[t.nmem] = r; ++t.nmem; }
+            }
+        }
+        SbTask &t = pl.task[nt++];
+        t.nrows = 4; t.kind = 3; t.nmem = 0;
+        t.x[0] = i; t.y[0] = i; t.x[1] = i; t.y[1] = j; t.x[2] = j; t.y[2] = i; t.x[3] = j; t.y[3] = j;
+        for (int q = 0; q < dd.nd; ++q)
+            for (int r = 0; r < dd.nd; ++r)
+                if (cls[q] && cls[r]) {
+                    t.mslot[t.nmem] = (cls[q] - 1) * 2 + (cls[r] - 1); t.mq[t.nmem] = q; t.mr[t.nmem] = r; ++t.nmem;
+                }
+        pl.skip = make_int4(nF > 0 ? F[0] : -1, nF > 1 ? F[1] : -1, nF > 2 ? F[2] : -1, nF > 3 ? F[3] : -1);
+        pl.skip_orbit4 = 1;
+    }
+    pl.ntasks = nt;
+}
+
+// One warp, one task, one slab: rotate the orbit (if any), write it back, and accumulate the super-block contributions
+// of its member rows into this warp's private accumulator.  Wn = the nd rows of W AFTER the rotation, in shared memory.
+__device__ __forceinline__ void run_sb_task(const SweepParams &p, const SbTask &tk, int al, bool rotated, double c, double s,
+                                            const double *Wn, int nd, double *sbw) {
+    const int n = p.n, lane = threadIdx.x & 31;
+    const long long n1 = n, n2 = n1 * n1, n3 = n2 * n1;
+    double *row[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) row[k] = p.S + al * n3 + tk.x[k < tk.nrows ? k : 0] * n2 + tk.y[k < tk.nrows ? k : 0] * n1;
+    double dot[4][4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dot[m][q] = 0.0;
+    const bool write = rotated && tk.nrows > 1;
+    for (int d = lane; d < n; d += 32) {
+        double v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (k < tk.nrows) ? __ldcg(row[k] + d) : 0.0;
+        if (write) {
+            if (tk.kind == 3) {
+                const double t0 = c * v[0] + s * v[1], t1 = c * v[1] - s * v[0], t2 = c * v[2] + s * v[3], t3 = c * v[3] - s * v[2];
+                v[0] = c * t0 + s * t2;     // (i, i)
+                v[2] = c * t2 - s * t0;     // (j, i)
+                v[1] = c * t1 + s * t3;     // (i, j)
+                v[3] = c * t3 - s * t1;     // (j, j)
+            } else {
+                const double x = v[0], y = v[1];
+                v[0] = c * x + s * y;
+                v[1] = c * y - s * x;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < tk.nrows) row[k][d] = v[k];
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (m < tk.nmem) {
+                const int sl = tk.mslot[m];
+                const double val = sl == 0 ? v[0] : sl == 1 ? v[1] : sl == 2 ? v[2] : v[3];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q < nd) dot[m][q] += val * Wn[q * n + d];
+            }
+    }
+    const int pl = (lane >> 2) & 3, sl = lane & 3;          // lanes 0..15 own (p, s)
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+        if (m < tk.nmem) {
+            double ds = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < nd) {
+                    const double t = warp_sum(dot[m][q]);
+                    if (sl == q) ds = t;
+                }
+            if (lane < 16 && pl < nd && sl < nd)
+                sbw[((pl * 4 + tk.mq[m]) * 4 + tk.mr[m]) * 4 + sl] += Wn[pl * n + p.a0 + al] * ds;
+        }
 }
 
 // B (24 doubles in smem) of the target pair from the super block: coefficient rows over D of the two targets.
@@ -268,44 +354,88 @@ __device__ __forceinline__ Target make_target(const Distinct &dd, int which_i, i
     }
     return t;
 }
-__device__ __forceinline__ void block_from_superblock(const double *sb /*[288] smem*/, const Target &t, double *blk) {
+// Dense 2 x 4 coefficient matrix of the two target orbitals over D (zeros where absent), built by one thread.
+__device__ __forceinline__ void target_matrix(const Target &t, double *T /*[2][4] smem*/) {
+    for (int k = 0; k < 8; ++k) T[k] = 0.0;
+    for (int k = 0; k < 2; ++k)
+        for (int a = 0; a < t.cnt[k]; ++a) T[k * 4 + t.idx[k][a]] += t.coef[k][a];
+}
+
+// B = T^(x4) SB as four single-index contractions (256 -> 128 -> 64 -> 32 -> 16 numbers) by SEARCH_THREADS threads
+// on the named barrier, plus the 2 x 2 x 2 gamma entries; then the polynomial coefficients of the pair cost.
+constexpr int SEARCH_THREADS = LS_THREADS;
+__device__ __forceinline__ void block_from_superblock(const double *sb /*[288] smem*/, const double *T /*[2][4]*/,
+                                                      double *tmp /*[192] smem*/, double *blk /*[24]*/, PairCoef &pc) {
     const int o = threadIdx.x;
-    if (o < 16) {
-        const int al = (o >> 3) & 1, be = (o >> 2) & 1, ga = (o >> 1) & 1, de = o & 1;
+    double *y1 = tmp, *y2 = tmp + 128;      // y1[p][q][r][de] (128), y2[p][q][ga][de] (64); y3 reuses y1
+    if (o < 128) {                          // contract s
+        const int de = o & 1, pqr = o >> 1;
         double acc = 0.0;
-        for (int a = 0; a < t.cnt[al]; ++a)
-            for (int b = 0; b < t.cnt[be]; ++b)
-                for (int c = 0; c < t.cnt[ga]; ++c)
-                    for (int d = 0; d < t.cnt[de]; ++d)
-                        acc += t.coef[al][a] * t.coef[be][b] * t.coef[ga][c] * t.coef[de][d] *
-                               sb[((t.idx[al][a] * 4 + t.idx[be][b]) * 4 + t.idx[ga][c]) * 4 + t.idx[de][d]];
-        blk[o] = acc;
-    } else if (o < 24) {
-        const int u = o - 16, spin = u >> 2, al = (u >> 1) & 1, be = u & 1;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) acc += T[de * 4 + s] * sb[pqr * 4 + s];
+        y1[o] = acc;
+    }
+    ls_sync<SEARCH_THREADS>();
+    if (o < 64) {                           // contract r
+        const int de = o & 1, ga = (o >> 1) & 1, pq = o >> 2;
         double acc = 0.0;
-        for (int a = 0; a < t.cnt[al]; ++a)
-            for (int b = 0; b < t.cnt[be]; ++b)
-                acc += t.coef[al][a] * t.coef[be][b] * sb[256 + spin * 16 + t.idx[al][a] * 4 + t.idx[be][b]];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc += T[ga * 4 + r] * y1[(pq * 4 + r) * 2 + de];
+        y2[o] = acc;
+    } else if (o >= 64 && o < 72) {         // gamma entries: spin, al, be
+        const int u = o - 64, spin = u >> 2, al = (u >> 1) & 1, be = u & 1;
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc += T[al * 4 + a] * T[be * 4 + c] * sb[256 + spin * 16 + a * 4 + c];
+        blk[16 + u] = acc;
+    }
+    ls_sync<SEARCH_THREADS>();
+    if (o < 32) {                           // contract q -> y3[p][be][ga][de] in y1
+        const int gd = o & 3, be = (o >> 2) & 1, pp = o >> 3;
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc += T[be * 4 + q] * y2[(pp * 4 + q) * 4 + gd];
+        y1[o] = acc;
+    }
+    ls_sync<SEARCH_THREADS>();
+    if (o < 16) {                           // contract p
+        const int rest = o & 7, al = o >> 3;
+        double acc = 0.0;
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) acc += T[al * 4 + pp] * y1[pp * 8 + rest];
         blk[o] = acc;
     }
+    ls_sync<SEARCH_THREADS>();
+    if (o == 0) make_coef(blk, pc);
+    ls_sync<SEARCH_THREADS>();
 }
 
 __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepParams p) {
-    __shared__ LineSearchSmemT<SW_THREADS> ls;
+    __shared__ LineSearchSmemT<SEARCH_THREADS> ls;
     __shared__ double blk[QIO_B200_BLOCK_DOUBLES];
     __shared__ double sb[SB_DOUBLES];
     __shared__ PairCoef pc;
     __shared__ double2 coarse_cs_sm[320];
     __shared__ int32_t fine_len_sm[320];
-    extern __shared__ double wrow_sm[];       // [4][n] rows of W for the super-block phase
-    const int n = p.n, tid = threadIdx.x;
+    __shared__ SbPlan plan;
+    __shared__ double Tmat[8];
+    __shared__ double sbtmp[192];
+    extern __shared__ double dyn_sm[];        // [4][n] rows of W after the rotation, then [SW_WARPS][256] accumulators
+    const int n = p.n, tid = threadIdx.x, warp = tid >> 5;
     const int G = gridDim.x, cta = blockIdx.x;
-    const int apc = max(4, (p.na + G - 1) / G);                   // leading-axis slabs per CTA in the super-block phase
-    const int K = (p.na + apc - 1) / apc;                         // CTAs with super-block work (K <= G)
+    double *Wn = dyn_sm, *sbw = dyn_sm + 4 * (size_t)n;
+    // super-block CTAs: CTAs 1..nsb (CTA 0 itself when the grid is a single CTA), apc slabs each
+    const int nsb = G > 1 ? max(1, min(G - 1, (p.na + 2) / 3)) : 1;
+    const int apc = (p.na + nsb - 1) / nsb;
+    const int sb_idx = G > 1 ? cta - 1 : 0;                       // index among the super-block CTAs
+    const bool is_sb_cta = (G == 1 || (cta >= 1 && cta <= nsb)) && sb_idx * apc < p.na;
+    const size_t pbuf_par = (size_t)(nsb + 1) * SB_DOUBLES;       // doubles per parity of pbuf
     unsigned epoch = 0;
     int accepted_total = 0, flags_or = 0;
-    unsigned long long tacc[6] = {0, 0, 0, 0, 0, 0}, t0 = 0, t1;
-    const bool timing = (cta == 0 && tid == 0);
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1;
+    const bool timing = ((cta == 0 || cta == 1 || cta == G - 3) && tid == 0);
 #define SW_TICK(slot)              \
     if (timing) {                  \
         t1 = gtimer();             \
@@ -328,6 +458,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepParams p) {
     // update CTAs: all but CTA 0 (which searches), unless the grid is a single CTA
     const int upd_ctas = G > 1 ? G - 1 : 1, upd_cta = G > 1 ? cta - 1 : 0;
     const long long gtid = (long long)upd_cta * SW_THREADS + tid, gthreads = (long long)upd_ctas * SW_THREADS;
+    double *Wbuf[2] = {p.W, p.W2};
 
     auto pair_at = [&](int t, int &i, int &j) {
         const int tt = t < p.P ? t : p.P - 1;
@@ -335,43 +466,84 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepParams p) {
         j = p.pairs[2 * tt + 1];
     };
 
-    // super block of step t (orbitals of pairs t and t+1) from the current state
-    auto phase_superblock = [&](int t) {
-        int i, j, i2, j2;
-        pair_at(t, i, j);
-        pair_at(t + 1, i2, j2);
-        const Distinct dd = make_distinct(i, j, i2, j2);
-        if (cta < K) superblock_partial(p, dd, cta, apc, wrow_sm, p.pbuf + (size_t)cta * SB_DOUBLES);
-        if (cta == (K < G ? K : 0) && tid < 32) {      // gamma entries over D (rank-replicated data)
+    // Super-block CTAs: partial super block over `dd` of the state AFTER rotation (i, j, c, s) -- the rotation of the
+    // orbits it owns is applied here -- into pbuf[par].  Wcur = W before the rotation.
+    auto phase_superblock = [&](const Distinct &dd, int i, int j, bool rotated, double c, double s, const double *Wcur,
+                                int par) {
+        for (int e = tid; e < dd.nd * n; e += SW_THREADS) {
+            const int q = e / n, d = e - q * n, x = dd.D[q];
+            double w;
+            if (rotated && x == i) w = c * __ldcg(Wcur + (size_t)i * n + d) + s * __ldcg(Wcur + (size_t)j * n + d);
+            else if (rotated && x == j) w = c * __ldcg(Wcur + (size_t)j * n + d) - s * __ldcg(Wcur + (size_t)i * n + d);
+            else w = __ldcg(Wcur + (size_t)x * n + d);
+            Wn[e] = w;
+        }
+        for (int e = tid; e < SW_WARPS * 256; e += SW_THREADS) sbw[e] = 0.0;
+        if (tid == 0) build_sb_plan(plan, dd, i, j, rotated);
+        __syncthreads();
+        const int first = sb_idx * apc, nslab = min(apc, p.na - first);
+        for (int slot = warp; slot < plan.ntasks * nslab; slot += SW_WARPS)
+            run_sb_task(p, plan.task[slot % plan.ntasks], first + slot / plan.ntasks, rotated, c, s, Wn, dd.nd, sbw + warp * 256);
+        __syncthreads();
+        if (tid < 256) {
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < SW_WARPS; ++w) acc += sbw[w * 256 + tid];
+            p.pbuf[par * pbuf_par + (size_t)sb_idx * SB_DOUBLES + tid] = acc;
+        }
+    };
+
+    // the designated CTA: gamma entries over dd (after its own in-place update of gamma) into pbuf[par]
+    auto publish_gamma_block = [&](const Distinct &dd, int par) {
+        if (tid < 32) {
             const int spin = tid >> 4, pp = (tid >> 2) & 3, qq = tid & 3;
             double v = 0.0;
             if (pp < dd.nd && qq < dd.nd)
                 v = __ldcg(p.gamma + (2 * (size_t)dd.D[pp] + spin) * (2 * (size_t)n) + 2 * dd.D[qq] + spin);
-            p.pbuf[(size_t)K * SB_DOUBLES + 256 + tid] = v;
+            p.pbuf[par * pbuf_par + (size_t)nsb * SB_DOUBLES + 256 + tid] = v;
         }
     };
 
-    // CTA 0: sum the partials in a fixed order (CTAs, then ranks) into shared memory
+    // CTA 0: sum the partials of parity `par` in a fixed order (CTAs, then ranks) into shared memory
     auto gather_superblock = [&](int t) {
+        const double *src = p.pbuf + (t & 1) * pbuf_par;
+        const int K = min(nsb, (p.na + apc - 1) / apc);
         if (tid < 256) {
-            double a8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};      // fixed pattern: deterministic on every rank
-            int c = 0;
-            for (; c + 8 <= K; c += 8) {
+            // 16 independent loads in flight per batch (the loads see loaded-L2 latency while the update streams);
+            // fixed summation pattern: deterministic and identical on every rank
+            double a16[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) a8[u] += __ldcg(p.pbuf + (size_t)(c + u) * SB_DOUBLES + tid);
+            for (int u = 0; u < 16; ++u) a16[u] = 0.0;
+            int c = 0;
+            for (; c + 16 <= K; c += 16) {
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (size_t)(c + u) * SB_DOUBLES + tid);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) a16[u] += v[u];
             }
-            for (int u = 0; c < K; ++c, ++u) a8[u] += __ldcg(p.pbuf + (size_t)c * SB_DOUBLES + tid);
-            sb[tid] = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+            {
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = (c + u < K) ? __ldcg(src + (size_t)(c + u) * SB_DOUBLES + tid) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) a16[u] += v[u];
+            }
+#pragma unroll
+            for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+                for (int u = 0; u < w; ++u) a16[u] += a16[u + w];
+            sb[tid] = a16[0];
         } else if (tid < 288) {
-            sb[tid] = __ldcg(p.pbuf + (size_t)K * SB_DOUBLES + tid);
+            sb[tid] = __ldcg(src + (size_t)nsb * SB_DOUBLES + tid);
         }
         if (p.nranks > 1) {
             // Every 16-byte word carries (value, tag): one NVLink store per element, no fence, no separate flag --
             // the receiver spins on the tag of each word it needs (the "LL" idea).  Slots alternate with the step
-            // parity; a slot is rewritten two steps later, after every reader has moved on (see the header comment).
+            // parity; a slot is rewritten two steps later, after every reader has moved on.
             const int par = t & 1;
             const unsigned long long tag = (p.epoch << 32) | (unsigned long long)(t + 1);
-            __syncthreads();
+            ls_sync<SEARCH_THREADS>();
             if (tid < 256) {
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(sb[tid]);
                 for (int dst = 0; dst < p.nranks; ++dst) {
@@ -392,103 +564,181 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepParams p) {
                 sb[tid] = acc;
             }
         }
-        __syncthreads();
+        ls_sync<SEARCH_THREADS>();
     };
 
-    // CTA 0: line search of pair `t` whose block is derived from the super block in smem
-    auto search_pair = [&](int t, const Target &tg) {
-        block_from_superblock(sb, tg, blk);
-        __syncthreads();
-        if (tid == 0) make_coef(blk, pc);
-        __syncthreads();
-        int i, j;
-        pair_at(t, i, j);
-        qio_b200_ls_result res;
-        cta_linesearch_t<SW_THREADS, PairCoef>(pc, p.inactive[i] != 0, p.inactive[j] != 0, tab, ls, res);
+    // CTA 0, threads < SEARCH_THREADS: line search of pair `t` (orbitals i, j) whose block is derived from the super
+    // block in smem.  All synchronisation inside is on the named barrier of the line search.
+    auto search_pair = [&](int t, int i, int j, const Target &tg) {
+        long long c0 = 0;
         if (tid == 0) {
+            c0 = clock64();
+            target_matrix(tg, Tmat);
+        }
+        const bool i_in = p.inactive[i] != 0, j_in = p.inactive[j] != 0;       // L2 latency overlaps the contraction
+        ls_sync<SEARCH_THREADS>();
+        block_from_superblock(sb, Tmat, sbtmp, blk, pc);
+        if (tid == 0) {
+            const long long c1 = clock64();
+            ls.prof[6] += c1 - c0;
+        }
+        qio_b200_ls_result res;
+        cta_linesearch_t<SEARCH_THREADS, PairCoef>(pc, i_in, j_in, tab, ls, res);
+        if (tid == 0) {
+            c0 = clock64();
             p.results[t] = res;
             p.cur[t & 1] = res;
+            ls.prof[7] += clock64() - c0;
         }
         accepted_total += res.accepted;
         flags_or |= res.flags;
     };
 
     if (p.P > 0) {
-        // ---- prologue: super block 0, search pair 0 -------------------------------------------------
+        // ---- prologue: second W buffer, super block 0 (no rotation pending), search pair 0 ---------------
         if (timing) t0 = gtimer();
-        phase_superblock(0);
-        grid_barrier(p.bar, G, epoch);
-        if (cta == 0) {
-            gather_superblock(0);
-            int i, j, i2, j2;
+        for (long long e = (long long)cta * SW_THREADS + tid; e < (long long)n * n; e += (long long)G * SW_THREADS)
+            p.W2[e] = __ldcg(p.W + e);
+        {
+            int i, j, i1, j1;
             pair_at(0, i, j);
-            pair_at(1, i2, j2);
-            const Distinct dd = make_distinct(i, j, i2, j2);
-            search_pair(0, make_target(dd, 0, 1, false, 1.0, 0.0));
+            pair_at(1, i1, j1);
+            const Distinct dd = make_distinct(i, j, i1, j1);
+            if (is_sb_cta) phase_superblock(dd, i, j, false, 1.0, 0.0, Wbuf[0], 0);
+            if (cta == cta_gamma) publish_gamma_block(dd, 0);
+            grid_barrier(p.bar, G, epoch);
+            if (cta == 0 && tid < SEARCH_THREADS) {
+                gather_superblock(0);
+                search_pair(0, i, j, make_target(dd, 0, 1, false, 1.0, 0.0));
+            }
+            grid_barrier(p.bar, G, epoch);
         }
-        grid_barrier(p.bar, G, epoch);
         SW_TICK(0)
 
         for (int t = 0; t < p.P; ++t) {
-            int i, j, i2, j2;
+            int i, j, i1, j1, i2, j2;
             pair_at(t, i, j);
-            pair_at(t + 1, i2, j2);
+            pair_at(t + 1, i1, j1);
+            pair_at(t + 2, i2, j2);
             const bool rotated = __ldcg(&p.cur[t & 1].accepted) != 0;
             const double c = __ldcg(&p.cur[t & 1].cos_theta), s = __ldcg(&p.cur[t & 1].sin_theta);
+            const bool need_sb = t + 2 < p.P;                 // SB_{t+1} feeds the search of pair t+2
+            const Distinct dd1 = make_distinct(i1, j1, i2, j2);
+            const double *Wcur = Wbuf[t & 1];
+            double *Wnext = Wbuf[(t + 1) & 1];
 
-            // ---- CTA 0: search pair t+1 from SB_t and theta_t ---------------------------------------
-            if (cta == 0 && t + 1 < p.P) {
-                const Distinct dd = make_distinct(i, j, i2, j2);
-                search_pair(t + 1, make_target(dd, 2, 3, rotated, c, s));
+            // ---- CTA 0: SB_t -> block of pair t+1 after rotation t -> line search -------------------------
+            if (cta == 0 && tid < SEARCH_THREADS) {
+                if (t > 0 && t + 1 < p.P) gather_superblock(t);
                 SW_TICK(1)
+                if (t + 1 < p.P) search_pair(t + 1, i1, j1, make_target(make_distinct(i, j, i1, j1), 2, 3, rotated, c, s));
+                SW_TICK(2)
             }
-            // ---- the other CTAs (or the only one): apply rotation t ----------------------------------
-            if ((G == 1 || cta != 0) && rotated) {
-                if ((n & 1) == 0)
-                    update_S<2>(p.S, n, p.na, i, j, c, s, gtid, gthreads);
-                else
-                    update_S<1>(p.S, n, p.na, i, j, c, s, gtid, gthreads);
-            }
-            if (rotated && cta == cta_gamma) {
-                // gamma <- V gamma V^T on the same-spin blocks: columns, then rows
-                const size_t ld = 2 * (size_t)n;
-                for (int k = tid; k < 2 * n; k += SW_THREADS) {
-                    const int a = k >> 1, spin = k & 1;
-                    double *row = p.gamma + (2 * (size_t)a + spin) * ld;
-                    butterfly1(row + 2 * i + spin, row + 2 * j + spin, c, s);
+            if (G == 1) __syncthreads();
+            // ---- the other CTAs (or the only one): rotation t ---------------------------------------------
+            if (G == 1 || cta != 0) {
+                int4 skip = make_int4(-1, -1, -1, -1);
+                bool skip4 = false;
+                if (need_sb) {
+                    if (is_sb_cta) {
+                        phase_superblock(dd1, i, j, rotated, c, s, Wcur, (t + 1) & 1);
+                        skip = plan.skip;
+                        skip4 = plan.skip_orbit4 != 0;
+                    } else if (rotated) {       // same plan, needed only for the rows to leave alone
+                        int nE = 0, nF = 0, F[4] = {-1, -1, -1, -1};
+                        for (int q = 0; q < dd1.nd; ++q) {
+                            if (dd1.D[q] == i || dd1.D[q] == j) ++nE;
+                            else F[nF++] = dd1.D[q];
+                        }
+                        if (nE > 0) {
+                            skip = make_int4(F[0], F[1], F[2], F[3]);
+                            skip4 = true;
+                        }
+                    }
                 }
-                __syncthreads();
-                for (int k = tid; k < 2 * n; k += SW_THREADS) {
-                    const int b = k >> 1, spin = k & 1;
-                    butterfly1(p.gamma + (2 * (size_t)i + spin) * ld + 2 * b + spin,
-                               p.gamma + (2 * (size_t)j + spin) * ld + 2 * b + spin, c, s);
+                if (cta == 1) { SW_TICK(4) }
+                // flat update: by the CTAs that own no super-block orbits in this step (all update CTAs otherwise)
+                // and not the two CTAs that carry the small replicated updates (they would be the stragglers)
+                const int nsb_active = (need_sb && G > 1) ? min(nsb, (p.na + apc - 1) / apc) : 0;
+                const int flat_ctas = upd_ctas - nsb_active - 2;
+                const bool split = G > 8 && flat_ctas >= upd_ctas / 4;
+                const long long f_threads = split ? (long long)flat_ctas * SW_THREADS : gthreads;
+                const long long f_tid = split ? (long long)(upd_cta - nsb_active) * SW_THREADS + tid : gtid;
+                if (rotated && f_tid >= 0 && f_tid < f_threads) {
+                    if ((n & 1) == 0)
+                        update_S<2>(p.S, n, p.na, i, j, c, s, f_tid, f_threads, skip, skip4);
+                    else
+                        update_S<1>(p.S, n, p.na, i, j, c, s, f_tid, f_threads, skip, skip4);
+                }
+                if (cta == 1 || cta == G - 3) { SW_TICK(5) }
+            }
+            if (cta == cta_gamma) {
+                if (rotated) {
+                    // gamma <- V gamma V^T on the same-spin blocks: columns, then rows
+                    const size_t ld = 2 * (size_t)n;
+                    for (int k = tid; k < 2 * n; k += SW_THREADS) {
+                        const int a = k >> 1, spin = k & 1;
+                        double *row = p.gamma + (2 * (size_t)a + spin) * ld;
+                        butterfly1(row + 2 * i + spin, row + 2 * j + spin, c, s);
+                    }
+                    __syncthreads();
+                    for (int k = tid; k < 2 * n; k += SW_THREADS) {
+                        const int b = k >> 1, spin = k & 1;
+                        butterfly1(p.gamma + (2 * (size_t)i + spin) * ld + 2 * b + spin,
+                                   p.gamma + (2 * (size_t)j + spin) * ld + 2 * b + spin, c, s);
+                    }
+                    __syncthreads();
+                }
+                if (need_sb) publish_gamma_block(dd1, (t + 1) & 1);
+            }
+            if (cta == cta_wu) {
+                // W (ping-pong: rows i, j rotated into the next buffer, plus the rows the previous step changed) and
+                // U rows i, j in place (U <- V U, jacobi.py:230)
+                int ip = -1, jp = -1;
+                if (t > 0) pair_at(t - 1, ip, jp);
+                for (int k = tid; k < n; k += SW_THREADS) {
+                    const double x = __ldcg(Wcur + (size_t)i * n + k), y = __ldcg(Wcur + (size_t)j * n + k);
+                    Wnext[(size_t)i * n + k] = rotated ? c * x + s * y : x;
+                    Wnext[(size_t)j * n + k] = rotated ? c * y - s * x : y;
+                    if (ip >= 0 && ip != i && ip != j) Wnext[(size_t)ip * n + k] = __ldcg(Wcur + (size_t)ip * n + k);
+                    if (jp >= 0 && jp != i && jp != j) Wnext[(size_t)jp * n + k] = __ldcg(Wcur + (size_t)jp * n + k);
+                    if (rotated) butterfly1(p.U + (size_t)i * n + k, p.U + (size_t)j * n + k, c, s);
                 }
             }
-            if (rotated && cta == cta_wu) {
-                // W and U rows i, j  (U <- V U, jacobi.py:230)
-                for (int k = tid; k < 2 * n; k += SW_THREADS) {
-                    double *M = (k < n) ? p.W : p.U;
-                    const int col = (k < n) ? k : k - n;
-                    butterfly1(M + (size_t)i * n + col, M + (size_t)j * n + col, c, s);
-                }
-            }
-            SW_TICK(2)
+            if (cta == 0) { SW_TICK(3) }
+            if (t == p.P / 2 && tid == 0) p.dbg[cta] = (double)(gtimer() % 1000000000ull);
             grid_barrier(p.bar, G, epoch);
-            SW_TICK(3)
-            if (t + 1 < p.P) {
-                phase_superblock(t + 1);
-                grid_barrier(p.bar, G, epoch);
-                SW_TICK(4)
-                if (cta == 0) gather_superblock(t + 1);
-                SW_TICK(5)
-            }
+            if (t == p.P / 2 && tid == 0) p.dbg[1024 + cta] = (double)(gtimer() % 1000000000ull);
+            if (cta == 0) { SW_TICK(6) } else { SW_TICK(7) }
         }
+        // the caller's W must hold the final rotation: it is Wbuf[P & 1]
+        if (p.P & 1)
+            for (long long e = (long long)cta * SW_THREADS + tid; e < (long long)n * n; e += (long long)G * SW_THREADS)
+                p.W[e] = __ldcg(p.W2 + e);
     }
     if (cta == 0 && tid == 0) {
         p.summary[0] = (double)accepted_total;
         p.summary[2] = (double)flags_or;
-        for (int k = 0; k < 6; ++k) p.summary[4 + k] = (double)tacc[k];
+        // CTA 0: [4] prologue, [5] gather, [6] search, [7] tail, [8] barrier wait
+        p.summary[4] = (double)tacc[0];
+        p.summary[5] = (double)tacc[1];
+        p.summary[6] = (double)tacc[2];
+        p.summary[7] = (double)tacc[3];
+        p.summary[8] = (double)tacc[6];
         for (int k = 0; k < 6; ++k) p.summary[10 + k] = (double)ls.prof[k];    // SM cycles inside the line search
+        p.summary[20] = (double)ls.prof[6];      // block from super block + coefficients + pair / mask loads
+        p.summary[21] = (double)ls.prof[7];      // result stores
+    }
+    if (cta == 1 && tid == 0) {
+        // CTA 1 (a super-block CTA): [16] super-block orbits, [17] flat update (if any), [18] barrier wait
+        p.summary[16] = (double)tacc[4];
+        p.summary[17] = (double)tacc[5];
+        p.summary[18] = (double)tacc[7];
+    }
+    if (G > 4 && cta == G - 3 && tid == 0) {
+        // CTA G-3 (a flat-update CTA): [22] flat update, [23] barrier wait
+        p.summary[22] = (double)tacc[5];
+        p.summary[23] = (double)tacc[7];
     }
 #undef SW_TICK
 }
@@ -538,10 +788,10 @@ __global__ void zero_offspin_if_kernel(double *gamma, int n, const double *summa
     }
 }
 
+constexpr size_t WS_HEADER = 256 + 2 * sizeof(qio_b200_ls_result) + 96;
+constexpr size_t WS_MAX_CTAS = 1024;     // one partial super block per CTA and parity; far above any SM count
 static size_t sweep_ws_bytes(int n) {
-    (void)n;
-    const size_t K = 1024;       // one partial super block per CTA; far above any SM count
-    return 256 + 2 * sizeof(qio_b200_ls_result) + 96 + sizeof(double) * (K + 1) * SB_DOUBLES;
+    return WS_HEADER + sizeof(double) * (2 * (WS_MAX_CTAS + 1) * SB_DOUBLES + (size_t)n * n + 2 * WS_MAX_CTAS);
 }
 
 }  // namespace qio
@@ -578,8 +828,8 @@ extern "C" int qio_b200_sweep_cycle(double *gamma, double *S, double *U, double 
     QIO_REQUIRE(nranks > 1 || (a0 == 0 && na == n), "sweep_cycle: a partial shard needs peers");
     cudaStream_t st = as_stream(stream);
     char *ws = reinterpret_cast<char *>(workspace);
-    QIO_CUDA(cudaMemsetAsync(ws, 0, 256 + 2 * sizeof(qio_b200_ls_result) + 96, st));
-    QIO_CUDA(cudaMemsetAsync(summary, 0, 16 * sizeof(double), st));
+    QIO_CUDA(cudaMemsetAsync(ws, 0, WS_HEADER, st));
+    QIO_CUDA(cudaMemsetAsync(summary, 0, 32 * sizeof(double), st));
     SweepParams p;
     p.S = S;
     p.gamma = gamma;
@@ -595,7 +845,9 @@ extern "C" int qio_b200_sweep_cycle(double *gamma, double *S, double *U, double 
     p.results = results;
     p.bar = reinterpret_cast<unsigned *>(ws);
     p.cur = reinterpret_cast<qio_b200_ls_result *>(ws + 256);
-    p.pbuf = reinterpret_cast<double *>(ws + 256 + 2 * sizeof(qio_b200_ls_result) + 96);
+    p.pbuf = reinterpret_cast<double *>(ws + WS_HEADER);
+    p.W2 = p.pbuf + 2 * (WS_MAX_CTAS + 1) * SB_DOUBLES;
+    p.dbg = p.W2 + (size_t)n * n;
     p.summary = summary;
     p.rank = h_peers ? h_peers->rank : 0;
     p.nranks = nranks;
@@ -603,16 +855,15 @@ extern "C" int qio_b200_sweep_cycle(double *gamma, double *S, double *U, double 
     p.mailboxes = nranks > 1 ? reinterpret_cast<double *const *>(h_peers->mailboxes) : nullptr;
     int blocks_per_sm = 0;
     QIO_REQUIRE(n <= 4096, "sweep_cycle: n too large for the shared-memory W rows");
-    if (sizeof(double) * 4 * (size_t)n > 32768)
-        QIO_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 4 * n)));
-    QIO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sweep_kernel, SW_THREADS, sizeof(double) * 4 * (size_t)n));
+    const size_t dyn_smem = sizeof(double) * (4 * (size_t)n + (size_t)SW_WARPS * 256);
+    QIO_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    QIO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sweep_kernel, SW_THREADS, dyn_smem));
     QIO_REQUIRE(blocks_per_sm >= 1, "sweep_cycle: kernel does not fit on an SM");
     const int grid = sm_count();
     QIO_REQUIRE(grid <= 1023, "sweep_cycle: workspace sized for at most 1023 CTAs");
     if (P > 0) {
         void *args[] = {&p};
-        QIO_CUDA(cudaLaunchCooperativeKernel((const void *)sweep_kernel, dim3(grid), dim3(SW_THREADS), args,
-                                             sizeof(double) * 4 * (size_t)n, st));
+        QIO_CUDA(cudaLaunchCooperativeKernel((const void *)sweep_kernel, dim3(grid), dim3(SW_THREADS), args, dyn_smem, st));
     }
     return QIO_B200_OK;
 }

@@ -218,7 +218,7 @@ def sweep_cycle(gamma, S, U, W, n, pairs, mask, tables, a0=0, na=None, peers=Non
     na = n if na is None else na
     P = int(pairs.shape[0])
     results = torch.empty(max(P, 1) * LS_DTYPE.itemsize, dtype=torch.uint8, device=require_cuda())
-    summary = empty(16)
+    summary = empty(32)
     ws = torch.empty(int(lib.qio_b200_sweep_workspace_bytes(n)), dtype=torch.uint8, device=require_cuda())
     if peers is not None:
         peers.next_epoch()
