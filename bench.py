@@ -53,7 +53,7 @@ def parse_args():
 def workload_config(n, n_gpus):
     return {
         'workload': f'synthetic determinant-ensemble rdm1/rdm2, n={n} orbitals (K=4, nocc={max(1, n // 5)}, seed 20261019+n), '
-                    f'inactive = all orbitals: prep_rdm12 + random-start rotation + all-pairs grad/Hess/line-search '
+                    f'inactive = all orbitals: prep_rdm12 + random-start rotation + all-pairs grad/Hess/line-search/pair-entropy '
                     f'+ one full Jacobi cycle',
         'n_orbitals': n,
         'pairs': n * (n - 1) // 2,
@@ -278,6 +278,7 @@ def run_b200_arm(args):
         blocks = dev.pair_blocks(g, Gamma, n, allpairs_d)
         dX, ddX = dev.fqi_grad_hess(blocks, n, mask)
         ls_all = dev.pair_linesearch(blocks, allpairs_d, mask, tabs)
+        s_pair, _, _ = dev.pair_entropy(blocks)          # extension a-9: pair entropies for the mutual-information matrix
         Ud = U0_d.clone()
         dev.sweep_reset(W, n)
         res, summary = dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs)
@@ -326,7 +327,7 @@ def run_b200_arm(args):
     clocks = sampler.stop()
     ms_per_step = ms_total / args.steps
     value = evals_per_step / (ms_per_step * 1e-3)
-    launches_per_step = 2 + 1 + 4 + 1 + 1 + 1 + (1 + 1 + 1 + 1 + 1) + 3   # prep, rotations, all-pairs, sweep (+cost), flush
+    launches_per_step = 2 + 1 + 4 + 1 + 1 + 1 + 1 + (1 + 1 + 1 + 1 + 1) + 3   # prep, rotations, all-pairs (+MI), sweep (+cost), flush
 
     # ---- phase timings (explain the step) and the roofline of the dominant kernel ----------------------
     def timed(fn, reps=1):
@@ -347,6 +348,7 @@ def run_b200_arm(args):
     phases['pair_blocks_ms'] = timed(lambda: dev.pair_blocks(g, Gamma, n, allpairs_d), 5)
     phases['grad_hess_ms'] = timed(lambda: dev.fqi_grad_hess(blocks, n, mask), 5)
     phases['linesearch_all_pairs_ms'] = timed(lambda: dev.pair_linesearch(blocks, allpairs_d, mask, tabs), 5)
+    phases['pair_entropy_mi_ms'] = timed(lambda: dev.pair_entropy(blocks), 5)
     Ud = U0_d.clone()
     dev.sweep_reset(W, n)
     sweep_ms = timed(lambda: dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs), 1)

@@ -225,6 +225,16 @@ int qio_b200_jacobi_cycle(double *gamma, double *Gamma, double *U, int n, const 
                           qio_b200_ls_result *results, double *summary, void *workspace,
                           void *stream);
 
+/* ---- a-9 (extension, no reference counterpart)  two-orbital RDM / mutual information ----------
+ * From the pair blocks: the 16 x 16 two-orbital RDM in its (N, S_z) blocks 1,2,2,1,4,1,2,2,1,
+ * closed with the 2-body data only (the nine 3- and 4-body expectation values listed in
+ * qio_b200/csrc/mi_formulas.inc are taken from `supp` (P, QIO_B200_MI_SUPP_DOUBLES) when given, else 0 --
+ * exact for two-electron states; same-spin 2-RDM entries use the singlet relation Gamma[abcd] - Gamma[abdc]).
+ * Block eigenvalues by cyclic Jacobi in registers; out: s_pair (P) and eig (P, 16). */
+#define QIO_B200_MI_SUPP_DOUBLES 9
+int qio_b200_pair_entropy(const double *blocks, const double *supp, int P, double *s_pair,
+                          double *eig, int32_t *flags, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,3 +37,4 @@ def install_as_qio():
     sys.modules['qio.grad.jacobi'] = grad.jacobi
     sys.modules['qio.grad.gradient'] = grad.gradient
     return this
+from . import mutual_info  # noqa: E402,F401  (extension: two-orbital RDM / mutual information)

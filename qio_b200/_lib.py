@@ -88,6 +88,7 @@ SIGNATURES = {
     'qio_b200_ipc_close': ([_p], _i),
     'qio_b200_ipc_free': ([_p], _i),
     'qio_b200_zero_offspin_if_rotated': ([_p, _i, _p, _p], _i),
+    'qio_b200_pair_entropy': ([_p, _p, _i, _p, _p, _p, _p], _i),
     'qio_b200_jacobi_workspace_bytes': ([_i, _i], ctypes.c_size_t),
     'qio_b200_jacobi_cycle': ([_p, _p, _p, _i, _p, _i, _p, ctypes.POINTER(ThetaTables), _p, _p, _p, _p], _i),
 }

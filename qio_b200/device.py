@@ -251,3 +251,12 @@ def sweep_flush(S, W, n, work=None):
     contract_axis(W, work, S, n, n3, last_axis=True)
     sweep_reset(W, n)
     return S
+
+
+def pair_entropy(blocks, supp=None):
+    """(s_pair (P), eig (P, 16), flags (P)) of the two-orbital RDMs built from the pair blocks (extension a-9)."""
+    P = int(blocks.shape[0])
+    s_pair, eig, flags = empty(P), empty(P, 16), empty(P, dtype=I32)
+    check(lib.qio_b200_pair_entropy(_ptr(blocks), _ptr(supp), P, _ptr(s_pair), _ptr(eig), _ptr(flags), _stream()),
+          'pair_entropy')
+    return s_pair, eig, flags

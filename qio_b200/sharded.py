@@ -154,13 +154,15 @@ class ShardedRDM:
         counts = [split_evenly(P, r, self.world)[1] - split_evenly(P, r, self.world)[0] for r in range(self.world)]
         g1, g2 = dev.pair_grad_hess(blocks[lo:hi], pairs[lo:hi], mask)
         rec = dev.pair_linesearch(blocks[lo:hi], pairs[lo:hi], mask, tables).reshape(hi - lo, LS_DTYPE.itemsize)
-        gh = allgather_rows(torch.stack([g1, g2], 1), counts, self.group)
+        s_pair, _, _ = dev.pair_entropy(blocks[lo:hi])                  # extension a-9 (mutual information)
+        gh = allgather_rows(torch.stack([g1, g2, s_pair], 1), counts, self.group)
         rec = allgather_rows(rec, counts, self.group)
         dX = torch.zeros((n, n), dtype=torch.float64, device=gh.device)
         ddX = torch.zeros_like(dX)
         i, j = pairs[:, 0].long(), pairs[:, 1].long()
         dX[i, j], dX[j, i] = gh[:, 0], -gh[:, 0]
         ddX[i, j], ddX[j, i] = gh[:, 1], gh[:, 1]
+        self.pair_entropy = gh[:, 2]                                    # S_ij in the order of all_pairs(n)
         return dX, ddX, rec.reshape(-1)
 
     # -- rotations -----------------------------------------------------------------------------------------
