@@ -132,36 +132,42 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_sample(n, n_ls_pairs=48, n_sweep_pairs=4):
+_CPU_SETUP = {}
+
+
+def cpu_reference_setup(n):
+    """Rotated synthetic RDMs and the sweep pair order on the host (built once per process)."""
+    if n not in _CPU_SETUP:
+        from oracle import qio_oracle as O
+        from qio_b200 import synth
+        t0 = time.time()
+        gamma0, Gamma0 = synth.prepared_rdms(n)
+        U0, order = sweep_order(n)
+        g = O.rotate_rdm1(U0, gamma0)
+        G = O.rotate_rdm2(U0, Gamma0)
+        inact = list(range(n))
+        _CPU_SETUP[n] = dict(g=g, G=G, inact=inact, pairs=O.sweep_pairs(order, inact), setup_s=time.time() - t0)
+    return _CPU_SETUP[n]
+
+
+def cpu_reference_sample(n, n_ls_pairs=48, n_sweep_pairs=4, offset=0):
     """Times the reference-shaped CPU path (oracle port: scalar jacobi_cost loop for the line search, dense
     einsum for jacobi_transform -- what qio/grad/jacobi.py executes) on a bounded sample and extrapolates the
     evals/s of the full step:  all-pairs pass = P line searches;  sweep = P x (line search + accepted transform)."""
     from oracle import qio_oracle as O
-    from qio_b200 import synth
-    t0 = time.time()
-    gamma0, Gamma0 = synth.prepared_rdms(n)
-    U0, order = sweep_order(n)
-    g = O.rotate_rdm1(U0, gamma0)
-    G = O.rotate_rdm2(U0, Gamma0)
-    setup_s = time.time() - t0
-    inact = list(range(n))
-    pairs = O.sweep_pairs(order, inact)
+    st = cpu_reference_setup(n)
+    g, G, inact, pairs = st['g'], st['G'], st['inact'], st['pairs']
     P = len(pairs)
+    sample = [pairs[(offset + k) % P] for k in range(n_ls_pairs)]
     # line searches (1 core, pure Python like the reference)
     t0 = time.time()
-    evals = 0
-    accepted = 0
-    thetas = []
-    for (i, j) in pairs[:n_ls_pairs]:
-        t = O.jacobi_direct_scalar(i, j, g, G, inact)
-        thetas.append(t)
-        accepted += t is not None
-        evals += 1 + 314 + 200
+    thetas = [O.jacobi_direct_scalar(i, j, g, G, inact) for (i, j) in sample]
     t_ls = (time.time() - t0) / n_ls_pairs
+    accepted = sum(t is not None for t in thetas)
     # dense transforms (BLAS threads)
     t0 = time.time()
     done = 0
-    for (i, j), t in zip(pairs[:n_sweep_pairs], thetas[:n_sweep_pairs]):
+    for (i, j), t in zip(sample[:n_sweep_pairs], thetas[:n_sweep_pairs]):
         O.jacobi_transform_dense(g, G, i, j, 0.1 if t is None else t)
         done += 1
     t_tr = (time.time() - t0) / max(done, 1)
@@ -175,7 +181,7 @@ def cpu_reference_sample(n, n_ls_pairs=48, n_sweep_pairs=4):
                    f'({t_ls * 1e3:.1f} ms each, 1 core) + {done} dense jacobi_transform einsums ({t_tr:.2f} s each, '
                    f'BLAS on {os.cpu_count()} cores); full step extrapolated as P*t_ls + P*(t_ls + {acc_rate:.2f}*t_tr) '
                    f'= {step_s:.0f} s for P={P} pairs'),
-        'line_search_ms': t_ls * 1e3, 'transform_s': t_tr, 'extrapolated_step_s': step_s, 'setup_s': setup_s,
+        'line_search_ms': t_ls * 1e3, 'transform_s': t_tr, 'extrapolated_step_s': step_s, 'setup_s': st['setup_s'],
     }
 
 
@@ -189,7 +195,7 @@ def run_reference_arm(args):
     t_start = time.time()
     for s in range(args.warmup + steps):
         # bounded sample per step so that the whole run stays within minutes
-        last = cpu_reference_sample(args.n, n_ls_pairs=12, n_sweep_pairs=1)
+        last = cpu_reference_sample(args.n, n_ls_pairs=48, n_sweep_pairs=2, offset=48 * s)
         if s >= args.warmup:
             vals.append(last['value'])
         if time.time() - t_start > 240 and vals:

@@ -4,7 +4,7 @@ pair entropies S_ij and the orbital mutual information I_ij = S_i + S_j - S_ij f
 From rdm1 / rdm2 alone the 16 x 16 two-orbital RDM is exact only when the 3- and 4-body expectation values on the
 pair vanish (two-electron states); a solver that can provide them passes a ``supplement`` of nine numbers per pair
 (listed in qio_b200/csrc/mi_formulas.inc).  Same-spin 2-RDM entries follow from the singlet relation.  Validated
-against brute-force partial traces only (oracle/mi_oracle.py) -- never reported as "matches the reference".
+against brute-force partial traces only (tests/test_gpu_mi.py) -- never reported as "matches the reference".
 """
 from __future__ import annotations
 
