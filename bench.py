@@ -40,7 +40,9 @@ def parse_args():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--n', type=int, default=100, help='number of orbitals (100 = configs[3], 200 = configs[4])')
+    # '--orbitals' is the spelling to use under torchrun: its own parser rejects '--n' as an ambiguous prefix
+    ap.add_argument('--n', '--orbitals', dest='n', type=int, default=int(os.environ.get('QIO_BENCH_N', '100')),
+                    help='number of orbitals (100 = configs[3], 200 = configs[4])')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')

@@ -27,6 +27,8 @@
 // The flush (W applied to axes 0 and 3 with two DMMA GEMM passes) happens once, when the caller wants Gamma back.
 #include <string.h>
 
+#include <type_traits>
+
 #include "linesearch.cuh"
 
 namespace qio {
@@ -137,24 +139,50 @@ struct Counter3 {
 // Work items are 16-byte words of d-rows, (slab, row, vector column) enumerated flat and grid-strided, so
 // that consecutive threads touch consecutive words.
 template <int V>
-__device__ __forceinline__ void update_S(double *__restrict__ S, int n, int na, int i, int j, double c, double s,
+static __device__ __noinline__ void update_S(double *__restrict__ S, int n, int na, int i, int j, double c, double s,
                                          long long gtid, long long gthreads, int4 skip, bool skip_orbit4) {
     const long long n1 = n, n2 = n1 * n1, n3 = n2 * n1;
     const int rowv = n / V;          // vector elements per d-row
     // axis 1: rows (a', {i,j}, cc, :) for all (a', cc), cc in {i, j} excluded (they belong to the 4-orbit)
-    // (`skip` lists up to four row indices whose orbits are owned by the super-block warps, -1 = none)
-    for (Counter3 k(gtid, gthreads, n, rowv); k.a < na; k.step()) {
-        if (k.r == i || k.r == j || k.r == skip.x || k.r == skip.y || k.r == skip.z || k.r == skip.w) continue;
-        double *px = S + k.a * n3 + (long long)i * n2 + k.r * n1 + (long long)k.v * V;
-        double *py = S + k.a * n3 + (long long)j * n2 + k.r * n1 + (long long)k.v * V;
-        if (V == 2) butterfly2(px, py, c, s); else butterfly1(px, py, c, s);
-    }
     // axis 2: rows (a', b, {i,j}, :) for all (a', b), b in {i, j} excluded
-    for (Counter3 k(gtid, gthreads, n, rowv); k.a < na; k.step()) {
-        if (k.r == i || k.r == j || k.r == skip.x || k.r == skip.y || k.r == skip.z || k.r == skip.w) continue;
-        double *px = S + k.a * n3 + k.r * n2 + (long long)i * n1 + (long long)k.v * V;
-        double *py = S + k.a * n3 + k.r * n2 + (long long)j * n1 + (long long)k.v * V;
-        if (V == 2) butterfly2(px, py, c, s); else butterfly1(px, py, c, s);
+    // (`skip` lists up to four row indices whose orbits are owned by the super-block warps, -1 = none)
+    // UNR butterflies (2 UNR independent 16-byte loads) are in flight per thread: the update is a latency x
+    // bandwidth product (Little's law), one butterfly per thread at a time leaves most of L2 / HBM idle.
+    constexpr int UNR = 4;
+    using VT = typename std::conditional<V == 2, double2, double>::type;
+#pragma unroll 1
+    for (int axis = 0; axis < 2; ++axis) {
+        const long long si = axis == 0 ? (long long)i * n2 : (long long)i * n1, sj = axis == 0 ? (long long)j * n2 : (long long)j * n1;
+        const long long sr = axis == 0 ? n1 : n2;
+        Counter3 k(gtid, gthreads, n, rowv);
+        while (k.a < na) {
+            long long off[UNR];          // element offset of the butterfly, -1 = nothing to do
+            VT x[UNR], y[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const bool ok = k.a < na && !(k.r == i || k.r == j || k.r == skip.x || k.r == skip.y || k.r == skip.z || k.r == skip.w);
+                off[u] = ok ? k.a * n3 + k.r * sr + (long long)k.v * V : -1;
+                k.step();
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (off[u] >= 0) {
+                    x[u] = __ldcg(reinterpret_cast<const VT *>(S + off[u] + si));
+                    y[u] = __ldcg(reinterpret_cast<const VT *>(S + off[u] + sj));
+                }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (off[u] >= 0) {
+                    VT *px = reinterpret_cast<VT *>(S + off[u] + si), *py = reinterpret_cast<VT *>(S + off[u] + sj);
+                    if constexpr (V == 2) {
+                        *px = make_double2(c * x[u].x + s * y[u].x, c * x[u].y + s * y[u].y);
+                        *py = make_double2(c * y[u].x - s * x[u].x, c * y[u].y - s * x[u].y);
+                    } else {
+                        *px = c * x[u] + s * y[u];
+                        *py = c * y[u] - s * x[u];
+                    }
+                }
+        }
     }
     // the 4-row orbit (a', {i,j}, {i,j}, :): both axes
     if (skip_orbit4) return;
@@ -272,7 +300,7 @@ __device__ __forceinline__ void build_sb_plan(SbPlan &pl, const Distinct &dd, in
 
 // One warp, one task, one slab: rotate the orbit (if any), write it back, and accumulate the super-block contributions
 // of its member rows into this warp's private accumulator.  Wn = the nd rows of W AFTER the rotation, in shared memory.
-__device__ __forceinline__ void run_sb_task(const SweepParams &p, const SbTask &tk, int al, bool rotated, double c, double s,
+static __device__ __noinline__ void run_sb_task(const SweepParams &p, const SbTask &tk, int al, bool rotated, double c, double s,
                                             const double *Wn, int nd, double *sbw) {
     const int n = p.n, lane = threadIdx.x & 31;
     const long long n1 = n, n2 = n1 * n1, n3 = n2 * n1;
@@ -285,35 +313,44 @@ __device__ __forceinline__ void run_sb_task(const SweepParams &p, const SbTask &
 #pragma unroll
         for (int q = 0; q < 4; ++q) dot[m][q] = 0.0;
     const bool write = rotated && tk.nrows > 1;
-    for (int d = lane; d < n; d += 32) {
-        double v[4];
+    // four 32-column chunks per trip: up to 16 independent loads per lane in flight (an orbit visit is latency-bound)
+    for (int d0 = lane; d0 < n; d0 += 128) {
+        double vv[4][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (k < tk.nrows) ? __ldcg(row[k] + d) : 0.0;
-        if (write) {
-            if (tk.kind == 3) {
-                const double t0 = c * v[0] + s * v[1], t1 = c * v[1] - s * v[0], t2 = c * v[2] + s * v[3], t3 = c * v[3] - s * v[2];
-                v[0] = c * t0 + s * t2;     // (i, i)
-                v[2] = c * t2 - s * t0;     // (j, i)
-                v[1] = c * t1 + s * t3;     // (i, j)
-                v[3] = c * t3 - s * t1;     // (j, j)
-            } else {
-                const double x = v[0], y = v[1];
-                v[0] = c * x + s * y;
-                v[1] = c * y - s * x;
+        for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) vv[ch][k] = (k < tk.nrows && d0 + 32 * ch < n) ? __ldcg(row[k] + d0 + 32 * ch) : 0.0;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            const int d = d0 + 32 * ch;
+            if (d >= n) break;
+            double *v = vv[ch];
+            if (write) {
+                if (tk.kind == 3) {
+                    const double t0 = c * v[0] + s * v[1], t1 = c * v[1] - s * v[0], t2 = c * v[2] + s * v[3], t3 = c * v[3] - s * v[2];
+                    v[0] = c * t0 + s * t2;     // (i, i)
+                    v[2] = c * t2 - s * t0;     // (j, i)
+                    v[1] = c * t1 + s * t3;     // (i, j)
+                    v[3] = c * t3 - s * t1;     // (j, j)
+                } else {
+                    const double x = v[0], y = v[1];
+                    v[0] = c * x + s * y;
+                    v[1] = c * y - s * x;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < tk.nrows) row[k][d] = v[k];
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k < tk.nrows) row[k][d] = v[k];
+            for (int m = 0; m < 4; ++m)
+                if (m < tk.nmem) {
+                    const int sl = tk.mslot[m];
+                    const double val = sl == 0 ? v[0] : sl == 1 ? v[1] : sl == 2 ? v[2] : v[3];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q < nd) dot[m][q] += val * Wn[q * n + d];
+                }
         }
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-            if (m < tk.nmem) {
-                const int sl = tk.mslot[m];
-                const double val = sl == 0 ? v[0] : sl == 1 ? v[1] : sl == 2 ? v[2] : v[3];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (q < nd) dot[m][q] += val * Wn[q * n + d];
-            }
     }
     const int pl = (lane >> 2) & 3, sl = lane & 3;          // lanes 0..15 own (p, s)
 #pragma unroll
