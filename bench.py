@@ -432,9 +432,14 @@ def run_b200_arm(args):
 
 
 def sweep_phase_table(tsum, npairs):
-    """Per-pair averages (us) of the phase timers the sweep kernel keeps on CTA 0 (search side) and CTA 1 (update side)."""
+    """Per-pair averages (us) of the phase timers the sweep kernel keeps."""
     us = lambda v: float(v) / 1e3 / max(npairs, 1)
-    return {'cta0_gather': us(tsum[5]), 'cta0_search': us(tsum[6]), 'cta0_tail': us(tsum[7]), 'cta0_barrier_wait': us(tsum[8]),
+    if len(tsum) > 24 and float(tsum[24]) == 3.0:      # pipelined kernel (sweep3.cu): timers of the search CTA
+        return {'engine': 3, 'cta0_wait_superblock': us(tsum[5]), 'cta0_setup_contract': us(tsum[9]), 'cta0_search': us(tsum[6]),
+                'cta0_publish': us(tsum[7]), 'worker0_wait_angle_plan': us(tsum[16]), 'worker0_step': us(tsum[17]),
+                'worker0_tile_phase': us(tsum[18]), 'worker0_pure_wait': us(tsum[19]), 'reducer0_wait': us(tsum[20]), 'reducer0_sum_publish': us(tsum[21]),
+                'worker0_tile_pass': us(tsum[22]), 'worker0_flat_thread128': us(tsum[23])}
+    return {'engine': 2, 'cta0_gather': us(tsum[5]), 'cta0_search': us(tsum[6]), 'cta0_tail': us(tsum[7]), 'cta0_barrier_wait': us(tsum[8]),
             'cta1_superblock_orbits': us(tsum[16]), 'cta1_flat_update': us(tsum[17]), 'cta1_barrier_wait': us(tsum[18]),
             'flatcta_update': us(tsum[22]), 'flatcta_barrier_wait': us(tsum[23]),
             'prologue_total_us': float(tsum[4]) / 1e3}

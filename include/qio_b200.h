@@ -196,6 +196,11 @@ typedef struct qio_b200_peers {
                                (own + cudaIpc-opened peers); each mailbox has qio_b200_mailbox_bytes(nranks) */
 } qio_b200_peers;
 size_t qio_b200_sweep_workspace_bytes(int n);
+/* Which kernel sweep_cycle runs for (n, na): 3 = pipelined (no grid barriers: column-owning worker CTAs, a reducer CTA and a
+ * search CTA that works three rotations ahead of the data it needs; used wherever a worker's columns of W fit in shared
+ * memory), 2 = one grid barrier per pair.  Same results records either way.  QIO_B200_SWEEP_ENGINE=2 forces the latter.
+ * summary[3] != 0 reports that a wait inside the pipelined kernel timed out (the cycle is then incomplete). */
+int qio_b200_sweep_engine(int n, int na);
 size_t qio_b200_mailbox_bytes(int nranks);
 int qio_b200_sweep_reset(double *W, int n, void *stream);
 int qio_b200_sweep_cycle(double *gamma, double *S, double *U, double *W, int n, int a0, int na,

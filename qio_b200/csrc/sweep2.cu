@@ -29,7 +29,10 @@
 
 #include <type_traits>
 
+#include <stdlib.h>
+
 #include "linesearch.cuh"
+#include "sweep3.cuh"
 
 namespace qio {
 
@@ -833,10 +836,24 @@ static size_t sweep_ws_bytes(int n) {
 
 }  // namespace qio
 
-extern "C" size_t qio_b200_sweep_workspace_bytes(int n) { return qio::sweep_ws_bytes(n); }
+// 3 = pipelined kernel without grid barriers (sweep3.cu), 2 = barrier kernel of this file.  QIO_B200_SWEEP_ENGINE=2|3
+// forces one (3 only where it fits); the default is 3 wherever the owned W columns fit in shared memory.
+static int sweep_engine(int n, int na) {
+    const char *e = getenv("QIO_B200_SWEEP_ENGINE");
+    if (e && e[0] == '2') return 2;
+    return qio::sweep3_supported(n, na) ? 3 : 2;
+}
+
+extern "C" int qio_b200_sweep_engine(int n, int na) { return sweep_engine(n, na); }
+
+extern "C" size_t qio_b200_sweep_workspace_bytes(int n) {
+    const size_t a = qio::sweep_ws_bytes(n), b = qio::sweep3_workspace_bytes(n);
+    return a > b ? a : b;
+}
 
 extern "C" size_t qio_b200_mailbox_bytes(int nranks) {
-    return sizeof(double) * 2 * (size_t)(nranks > 0 ? nranks : 1) * qio::MB_STRIDE;
+    const size_t a = sizeof(double) * 2 * (size_t)(nranks > 0 ? nranks : 1) * qio::MB_STRIDE, b = qio::sweep3_mailbox_bytes(nranks);
+    return a > b ? a : b;
 }
 
 extern "C" int qio_b200_sweep_reset(double *W, int n, void *stream) {
@@ -864,6 +881,8 @@ extern "C" int qio_b200_sweep_cycle(double *gamma, double *S, double *U, double 
     QIO_REQUIRE(nranks == 1 || (h_peers->mailboxes && h_peers->rank >= 0 && h_peers->rank < nranks), "sweep_cycle: bad peers");
     QIO_REQUIRE(nranks > 1 || (a0 == 0 && na == n), "sweep_cycle: a partial shard needs peers");
     cudaStream_t st = as_stream(stream);
+    if (sweep_engine(n, na) == 3)
+        return sweep3_launch(gamma, S, U, W, n, a0, na, pairs, P, inactive, h_tables, results, summary, workspace, h_peers, st);
     char *ws = reinterpret_cast<char *>(workspace);
     QIO_CUDA(cudaMemsetAsync(ws, 0, WS_HEADER, st));
     QIO_CUDA(cudaMemsetAsync(summary, 0, 32 * sizeof(double), st));

@@ -1,0 +1,1139 @@
+// a-7 (pipelined path)  The Jacobi cycle as ONE persistent kernel WITHOUT grid barriers.
+//
+// Same deferred-axis state as sweep2.cu:  Gamma_cur[a,b,c,d] = sum_{a',d'} W[a,a'] W[d,d'] S[a',b,c,d'],  axes 1, 2 of S in
+// the current basis, axes 0 (sharded) and 3 (contiguous) deferred through W.  What changes is who waits for whom.
+//
+//  * Ownership.  A Givens rotation of axes 1, 2 never mixes the leading index a' or the last index d'.  Every worker CTA
+//    therefore OWNS a fixed range of (slab, d') columns of S (a few hundred bytes of every d-row) and is the only CTA that
+//    ever reads or writes it: consecutive rotations need no grid-wide ordering at all, a worker only needs the angle.
+//  * Lookahead.  The block of pair k after rotations 0..k-1 is a linear image of the "super block" P_k over the <= 6
+//    orbitals of pairs k-2, k-1, k taken from the state after rotation k-3:
+//        P_k[p,q,r,s] = sum_{a'} W[D_p,a'] ( S[a',D_q,D_r,:] . W[D_s,:] ),     B_k = T^(x4) P_k,
+//    T = the two target orbitals after rotations k-2 and k-1 in terms of the orbitals before them (2 x |D|, built from the
+//    two angles the search CTA has just found).  So the search CTA needs from the rest of the machine only data that is
+//    three rotations old: it runs search after search back to back, and the workers, the reduction and (with peers) the
+//    NVLink exchange have a full search period of slack.
+//  * Roles.  CTA 0 searches (320 threads) and prefetches the next super block (192 threads).  CTAs 1..4 reduce the workers'
+//    partial super blocks in a fixed order and publish the total (to every rank's mailbox when sharded).  CTA 5 keeps the
+//    small replicated state (gamma, U, W) and publishes the gamma part of the super block.  CTAs 6.. are workers: wait for
+//    angle w -> rotate the rows of the next super block (P_{w+3}) inside their columns, take the dot products with their
+//    columns of W (kept in shared memory, rotated locally) -> post the partial -> stream the rest of rotation w.
+//  * Signalling is one-directional and tagged: angle records and totals are 16-byte (value, tag) words written with a
+//    single store and polled by the consumer ("LL" style), partial arrivals are a monotone counter.  Slot counts follow from
+//    how far the parties can drift apart (see the constants).  Every wait has a time-out that aborts the whole kernel.
+//
+// The launch is cooperative only to guarantee that all CTAs are co-resident.  Cases whose W columns do not fit in shared
+// memory (n = 200 on one GPU) stay on the barrier kernel of sweep2.cu (see qio_b200_sweep_cycle).
+#include <string.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "linesearch.cuh"
+#include "sweep3.cuh"
+
+namespace qio {
+namespace s3 {
+
+constexpr int THREADS = 512;
+constexpr int WARPS = THREADS / 32;
+constexpr int SEARCH_THREADS = LS_THREADS;          // 320: warps 0..9 of CTA 0
+constexpr int FETCH_THREADS = THREADS - LS_THREADS; // 192: warps 10..15 of CTA 0
+constexpr int MAXM = 6;                             // orbitals of three consecutive pairs
+constexpr int MAXE = 8;                             // ... plus the two of the rotation being applied
+constexpr int SB_MAX = MAXM * MAXM * MAXM * MAXM;   // 1296
+constexpr int GM_MAX = 2 * MAXM * MAXM;             // 72 gamma entries (spin, p, q)
+constexpr int TOT_WORDS = SB_MAX + GM_MAX;
+constexpr int LOOK = 3;          // P_k is taken from the state after rotation k - LOOK
+constexpr int SLOTS = 4;         // partial / total slots: a worker writes P_{w+3} only after the reducer finished P_w
+constexpr int MB_SLOTS = 8;      // mailbox slots: rank A may post P_{j+2} while rank B still reads P_{j-2}
+constexpr int RING = 8;          // angle records: the search CTA is at most LOOK records ahead of the slowest reader
+constexpr int MAX_PIECES = 4;
+constexpr int TILE_LEN = 96;     // owned columns handled per super-block tile
+constexpr int TILE_PITCH = 98;   // row pitch of the tile: 196 words = 4 mod 32, the 8 rows a warp reads fall on different banks
+constexpr int DT_STRIDE = 16;     // ints per entry of the per-pair table
+constexpr int DOT_THREADS = 128;  // threads of a worker that finish the super block while the others stream the update
+constexpr int NRED = 4;          // reducer CTAs (each sums a quarter of the entries)
+constexpr unsigned long long TIMEOUT_NS = 4000000000ull;
+constexpr int AUX_CTA = NRED + 1;
+constexpr int FIRST_WORKER = NRED + 2;
+
+struct Params {
+    double *S, *gamma, *U, *W;
+    int n, a0, na;
+    const int32_t *pairs;
+    int P;
+    const int32_t *inactive;
+    ThetaTablesDev tab;
+    qio_b200_ls_result *results;
+    double *summary;
+    unsigned long long *ring;   // [RING][4]: (cos bits, tag), (sin bits, tag); tag = 2 (k + 1) + accepted
+    unsigned *abort_flag;
+    unsigned long long *pbuf;   // [SLOTS][nworkers][SB_MAX][2] tagged partial entries (value bits, (launch << 32) | (k + 1))
+    unsigned long long launch_id;
+    unsigned long long *tot;    // [SLOTS][TOT_WORDS][2] (value bits, tag = k + 1)
+    int rank, nranks;
+    unsigned long long epoch;
+    double *const *mailboxes;   // [nranks] bases, layout [MB_SLOTS][nranks][SB_MAX][2]
+    const int32_t *dtab;        // [P][DT_STRIDE] per-pair table (see build_dtab_kernel)
+    int nworkers;               // workers that own at least one column
+    int granule;                // doubles per ownership quantum (4, 2 or 1)
+    int wc_cols;                // row pitch of a worker's private W columns
+    double *wg;                 // [nworkers][n][wc_cols] every worker's own columns of W (global, L2-resident, private)
+};
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void ll_store(unsigned long long *w, unsigned long long bits, unsigned long long tag) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(w), "l"(bits), "l"(tag) : "memory");
+}
+__device__ __forceinline__ void ll_load(const unsigned long long *w, unsigned long long &bits, unsigned long long &tag) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tag) : "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
+template <int COUNT>
+__device__ __forceinline__ void named_sync_id(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(COUNT) : "memory");
+}
+template <int COUNT>
+__device__ __forceinline__ void named_arrive_id(int id) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(COUNT) : "memory");
+}
+
+// Spin until pred() holds; false on time-out or when another CTA has aborted.
+template <typename Pred>
+__device__ __forceinline__ bool spin_until(const Params &p, Pred pred) {
+    if (pred()) return true;
+    const unsigned long long t0 = gtimer();
+    unsigned it = 0;
+    for (;;) {
+        if (pred()) return true;
+        if ((++it & 0xff) == 0) {
+            if (ld_volatile_u32(p.abort_flag) != 0) return false;
+            if (gtimer() - t0 > TIMEOUT_NS) {
+                atomicExch(p.abort_flag, 1u);
+                return false;
+            }
+        }
+    }
+}
+
+// ---- the orbitals of pairs lo..hi in order of first appearance -----------------------------------------------------
+struct DSet {
+    int m;
+    int D[MAXM];
+};
+__device__ __forceinline__ void make_dset(DSet &d, const int32_t *pairs, int lo, int hi) {
+    d.m = 0;
+    for (int k = lo; k <= hi; ++k)
+        for (int h = 0; h < 2; ++h) {
+            const int x = pairs[2 * k + h];
+            bool found = false;
+            for (int q = 0; q < d.m; ++q) found |= (d.D[q] == x);
+            if (!found) d.D[d.m++] = x;
+        }
+}
+__device__ __forceinline__ int dset_pos(const DSet &d, int x) {
+    int r = -1;
+    for (int q = 0; q < d.m; ++q)
+        if (d.D[q] == x) r = q;
+    return r;
+}
+// super block k covers pairs max(0, k - LOOK + 1) .. k
+__device__ __forceinline__ int sb_lo(int k) { return k - (LOOK - 1) > 0 ? k - (LOOK - 1) : 0; }
+
+// Per-pair table, built once per launch from the pair list (everything in it is independent of the angles):
+//   [0] m = |D_k|, [1..6] D_k (orbitals of pairs k-2..k in order of first appearance), [7], [8] position of i_k, j_k in D_k,
+//   [9], [10] position of (i, j) of pair k-2, [11], [12] of pair k-1 (-1 if that pair does not exist), [13], [14] inactive
+//   flags of i_k, j_k.
+__global__ void build_dtab_kernel(const int32_t *__restrict__ pairs, const int32_t *__restrict__ inactive, int P,
+                                  int32_t *__restrict__ dtab) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    DSet d;
+    make_dset(d, pairs, sb_lo(k), k);
+    int32_t *t = dtab + (size_t)k * DT_STRIDE;
+    t[0] = d.m;
+    for (int q = 0; q < MAXM; ++q) t[1 + q] = q < d.m ? d.D[q] : -1;
+    const int i = pairs[2 * k], j = pairs[2 * k + 1];
+    t[7] = dset_pos(d, i);
+    t[8] = dset_pos(d, j);
+    for (int h = 0; h < 2; ++h) {
+        const int v = k - 2 + h;
+        t[9 + 2 * h] = v >= 0 ? dset_pos(d, pairs[2 * v]) : -1;
+        t[10 + 2 * h] = v >= 0 ? dset_pos(d, pairs[2 * v + 1]) : -1;
+    }
+    t[13] = inactive[i] != 0;
+    t[14] = inactive[j] != 0;
+    t[15] = 0;
+}
+
+// Angle record k.  Returns false on abort.
+__device__ __forceinline__ bool read_record(const Params &p, int k, int &accepted, double &c, double &s) {
+    const unsigned long long *w = p.ring + (size_t)(k & (RING - 1)) * 4;
+    unsigned long long cb = 0, sbits = 0, t0 = 0, t1 = 0;
+    const unsigned long long want = 2ull * (unsigned long long)(k + 1);
+    const bool ok = spin_until(p, [&]() {
+        ll_load(w, cb, t0);
+        ll_load(w + 2, sbits, t1);
+        return (t0 >> 1) == (want >> 1) && t0 == t1;
+    });
+    accepted = (int)(t0 & 1ull);
+    c = __longlong_as_double((long long)cb);
+    s = __longlong_as_double((long long)sbits);
+    return ok;
+}
+
+// =====================================================================================================================
+// Workers
+// =====================================================================================================================
+struct Piece {
+    int slab;       // local slab index
+    int d0, len;    // columns [d0, d0 + len) of every d-row of that slab
+    int col0;       // first of its columns in the worker's concatenated column space (= in the shared-memory W columns)
+    int slabcol;    // column of W[:, a0 + slab] in the shared-memory W columns
+    long long base; // slab * n^3 + d0 - col0: element offset of concatenated column 0 of row (0, 0)
+};
+
+struct WorkerStep {             // built by thread 0 of a worker for each step, read by all its threads
+    int rotated, i, j;
+    double c, s;
+    int m;                      // orbitals of the super block produced in this step (0: none)
+    int D[MAXM];
+    int e;                      // tile orbitals: [i, j] (if rotated) followed by the orbitals of D other than i, j
+    int E[MAXE];
+    int tpos[MAXM];             // position of D_q in E
+    int slot;                   // super-block index (k) this step produces, -1 if none
+    int alive;
+};
+
+struct WorkerSmem {
+    Piece piece[MAX_PIECES];
+    int npieces, ncols, ncd;    // ncd = owned d-columns (concatenated over the pieces); ncols = ncd + npieces
+    WorkerStep st;
+    unsigned long long t_tile, t_wait, t_pass, t_flat;
+    unsigned skipmask[128];     // bit x: rows with index x are handled by the tile phase of this step (n <= 4096)
+    double dots[MAX_PIECES * MAXM * MAXM * MAXM];       // [piece][q][r][s]
+    alignas(16) double tile[MAXE * MAXE * TILE_PITCH];
+};
+
+__device__ __forceinline__ int piece_of(const WorkerSmem &sm, int cc) {
+    int pc = 0;
+#pragma unroll
+    for (int k = 1; k < MAX_PIECES; ++k)
+        if (k < sm.npieces && cc >= sm.piece[k].col0) pc = k;
+    return pc;
+}
+
+// Flat phase of a worker: items [first, last) of the (axis, x, vector column) space of its owned columns, strided over
+// `nt` threads (this one is number t): rows (i, x), (j, x) (axis 0) or (x, i), (x, j) (axis 1) rotated by (c, s).  Rows whose
+// bit is set in `skipmask` belong to the tile phase.  A separate function on purpose: its loop wants a clean register file
+// (four butterflies = eight independent 16-byte loads in flight per thread).
+template <int V>
+static __device__ __noinline__ void flat_update(double *__restrict__ S, const WorkerSmem *smp, int n, int i, int j, double c,
+                                                double s, long long first, long long last, int t, int nt) {
+    using VT = typename std::conditional<V == 2, double2, double>::type;
+    constexpr int UNR = 4;
+    const WorkerSmem &sm = *smp;
+    const long long n1 = n, n2 = n1 * n1;
+    const int lv = sm.ncd / V;
+    const long long b0 = sm.piece[0].base, b1 = sm.piece[1].base, b2 = sm.piece[2].base, b3 = sm.piece[3].base;
+    const int c1 = sm.npieces > 1 ? sm.piece[1].col0 : 0x7fffffff, c2 = sm.npieces > 2 ? sm.piece[2].col0 : 0x7fffffff,
+              c3 = sm.npieces > 3 ? sm.piece[3].col0 : 0x7fffffff;
+    // mixed-radix counter (rho2, v) advanced by nt items
+    const int dq = nt / lv, dr = nt - dq * lv;
+    long long item = first + t;
+    int rho2 = (int)(item / lv), v = (int)(item - (long long)rho2 * lv);
+    while (item < last) {
+        long long off[UNR];
+        VT x[UNR], y[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const bool in = item < last;
+            const int axis = rho2 >= n ? 1 : 0, xx = in ? rho2 - axis * n : 0;
+            const bool skip = !in || ((sm.skipmask[xx >> 5] >> (xx & 31)) & 1u);
+            const int cc = v * V;
+            const long long pb = cc >= c3 ? b3 : (cc >= c2 ? b2 : (cc >= c1 ? b1 : b0));
+            // bit 62 of the offset carries the axis
+            off[u] = skip ? -1 : ((pb + cc + (axis ? xx * n2 : xx * n1)) | ((long long)axis << 62));
+            item += nt;
+            v += dr;
+            rho2 += dq;
+            if (v >= lv) {
+                v -= lv;
+                ++rho2;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+            if (off[u] >= 0) {
+                const bool ax = (off[u] >> 62) & 1;
+                const long long o = off[u] & ~(1LL << 62);
+                const long long si = ax ? (long long)i * n1 : (long long)i * n2, sj = ax ? (long long)j * n1 : (long long)j * n2;
+                x[u] = __ldcg(reinterpret_cast<const VT *>(S + o + si));
+                y[u] = __ldcg(reinterpret_cast<const VT *>(S + o + sj));
+            }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+            if (off[u] >= 0) {
+                const bool ax = (off[u] >> 62) & 1;
+                const long long o = off[u] & ~(1LL << 62);
+                const long long si = ax ? (long long)i * n1 : (long long)i * n2, sj = ax ? (long long)j * n1 : (long long)j * n2;
+                if constexpr (V == 2) {
+                    *reinterpret_cast<VT *>(S + o + si) = make_double2(c * x[u].x + s * y[u].x, c * x[u].y + s * y[u].y);
+                    *reinterpret_cast<VT *>(S + o + sj) = make_double2(c * y[u].x - s * x[u].x, c * y[u].y - s * x[u].y);
+                } else {
+                    *reinterpret_cast<VT *>(S + o + si) = c * x[u] + s * y[u];
+                    *reinterpret_cast<VT *>(S + o + sj) = c * y[u] - s * x[u];
+                }
+            }
+    }
+}
+
+// One worker step: rotation (i, j, c, s) (if accepted) of the owned columns, producing the partial of super block `slot`
+// (if any) on the way.  Wg = the owned columns of W (private global copy, rotated here as well); Wr = shared-memory cache of
+// its rows E (the only ones a step reads), row t <-> orbital E[t].
+template <int V>
+__device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, double *Wg, double *Wr, int widx) {
+    using VT = typename std::conditional<V == 2, double2, double>::type;
+    const int tid = threadIdx.x;
+    const int n = p.n;
+    const long long n1 = n, n2 = n1 * n1;
+    const WorkerStep &st = sm.st;
+    const bool rot = st.rotated != 0;
+    const double c = st.c, s = st.s;
+    const int i = st.i, j = st.j, m = st.m, e = st.e, pitch = p.wc_cols;
+    const unsigned long long t_begin = (widx == 0 && tid == 0) ? gtimer() : 0;
+    auto bf = [&](VT &x, VT &y) {
+        if constexpr (V == 2) {
+            const VT nx_ = make_double2(c * x.x + s * y.x, c * x.y + s * y.y);
+            const VT ny_ = make_double2(c * y.x - s * x.x, c * y.y - s * x.y);
+            x = nx_;
+            y = ny_;
+        } else {
+            const VT nx_ = c * x + s * y, ny_ = c * y - s * x;
+            x = nx_;
+            y = ny_;
+        }
+    };
+
+    // ---- W columns: rows E into shared memory, rows i, j rotated on the way (and written back) -----------------
+    // (these loads share the latency window of the tile pass below; the barrier after the tile pass covers them)
+    {
+        const int f0 = rot ? 2 : 0;
+        if (rot)
+            for (int col = tid; col < sm.ncols; col += THREADS) {
+                double *gi = Wg + (size_t)i * pitch + col, *gj = Wg + (size_t)j * pitch + col;
+                const double x = __ldcg(gi), y = __ldcg(gj);
+                const double xn = c * x + s * y, yn = c * y - s * x;
+                *gi = xn;
+                *gj = yn;
+                Wr[col] = xn;
+                Wr[pitch + col] = yn;
+            }
+        if (m > 0)
+            for (int idx = tid; idx < (e - f0) * sm.ncols; idx += THREADS) {
+                const int t = f0 + idx / sm.ncols, col = idx - (t - f0) * sm.ncols;
+                Wr[(size_t)t * pitch + col] = __ldcg(Wg + (size_t)sm.st.E[t] * pitch + col);
+            }
+    }
+
+    // ---- tile phase: the rows (x, y), x, y in E, of all owned columns ------------------------------------------
+    // orbits of the rotation inside E x E: X = {IJ} + F (rotated) or X = E (not rotated); an orbit has 1, 2 or 4 rows
+    const int nx = rot ? e - 1 : e;              // size of X
+    const int m3 = m * m * m, ndot = sm.npieces * m3;
+    const unsigned long long ptag = (p.launch_id << 32) | (unsigned long long)(st.slot + 1);
+    unsigned long long *pslot = p.pbuf + ((size_t)(st.slot & (SLOTS - 1)) * p.nworkers + widx) * SB_MAX * 2;
+    auto tile_pass = [&](int t0, int tl) {
+        const int tv = tl / V, nitems = nx * nx * tv;
+        for (int item = tid; item < nitems; item += THREADS) {
+            const int orb = item / tv, v = item - orb * tv;
+            const int x1 = orb / nx, x2 = orb - x1 * nx;
+            const bool two1 = rot && x1 == 0, two2 = rot && x2 == 0;
+            const int ea0 = rot ? (x1 == 0 ? 0 : x1 + 1) : x1, eb0 = rot ? (x2 == 0 ? 0 : x2 + 1) : x2;   // E positions
+            const int oa0 = sm.st.E[ea0], ob0 = sm.st.E[eb0];
+            const int cc = t0 + v * V;
+            double *g = p.S + sm.piece[piece_of(sm, cc)].base + cc + oa0 * n2 + ob0 * n1;
+            const long long dj1 = (long long)(j - oa0) * n2, dj2 = (long long)(j - ob0) * n1;   // to the partner rows
+            VT q0, q1, q2, q3;      // rows (a, b), (a, j), (j, b), (j, j)
+            q0 = __ldcg(reinterpret_cast<const VT *>(g));
+            if (two2) q1 = __ldcg(reinterpret_cast<const VT *>(g + dj2));
+            if (two1) q2 = __ldcg(reinterpret_cast<const VT *>(g + dj1));
+            if (two1 && two2) q3 = __ldcg(reinterpret_cast<const VT *>(g + dj1 + dj2));
+            if (two1 && two2) {
+                bf(q0, q1);       // axis 2 on row i
+                bf(q2, q3);       // axis 2 on row j
+                bf(q0, q2);       // axis 1 on column i
+                bf(q1, q3);       // axis 1 on column j
+                *reinterpret_cast<VT *>(g) = q0;
+                *reinterpret_cast<VT *>(g + dj2) = q1;
+                *reinterpret_cast<VT *>(g + dj1) = q2;
+                *reinterpret_cast<VT *>(g + dj1 + dj2) = q3;
+            } else if (two1) {
+                bf(q0, q2);
+                *reinterpret_cast<VT *>(g) = q0;
+                *reinterpret_cast<VT *>(g + dj1) = q2;
+            } else if (two2) {
+                bf(q0, q1);
+                *reinterpret_cast<VT *>(g) = q0;
+                *reinterpret_cast<VT *>(g + dj2) = q1;
+            }
+            if (m > 0) {
+                *(reinterpret_cast<VT *>(sm.tile + (ea0 * e + eb0) * TILE_PITCH) + v) = q0;
+                if (two2) *(reinterpret_cast<VT *>(sm.tile + (ea0 * e + 1) * TILE_PITCH) + v) = q1;
+                if (two1) *(reinterpret_cast<VT *>(sm.tile + (1 * e + eb0) * TILE_PITCH) + v) = q2;
+                if (two1 && two2) *(reinterpret_cast<VT *>(sm.tile + (1 * e + 1) * TILE_PITCH) + v) = q3;
+            }
+        }
+    };
+    // dot (piece, q, r, s) over the columns [t0, t0 + tl) of the tile; s varies fastest over the lanes (same tile element:
+    // broadcast), the rows a warp reads sit on different banks (TILE_PITCH)
+    auto tile_dot = [&](int idx, int t0, int tl) -> double {
+        const int pc = idx / m3, qrs = idx - pc * m3, qr = qrs / m, ss = qrs - qr * m, q = qr / m, r = qr - q * m;
+        const Piece P = sm.piece[pc];
+        const int lo = max(P.col0, t0), hi = min(P.col0 + P.len, t0 + tl);
+        const double *row = sm.tile + (sm.st.tpos[q] * e + sm.st.tpos[r]) * TILE_PITCH - t0;
+        const double *wrow = Wr + (size_t)sm.st.tpos[ss] * pitch;
+        double a0 = 0.0, a1 = 0.0;
+        int d = lo;
+        for (; d + 1 < hi; d += 2) {
+            a0 += row[d] * wrow[d];
+            a1 += row[d + 1] * wrow[d + 1];
+        }
+        if (d < hi) a0 += row[d] * wrow[d];
+        return a0 + a1;
+    };
+    // entry (p, q, r, s) = sum over the pieces of W[D_p, slab] * dot(piece, q, r, s), posted as a tagged 16-byte word
+    auto post_entry = [&](int en) {
+        const int pp = en / m3, qrs = en - pp * m3;
+        const double *wrow = Wr + (size_t)sm.st.tpos[pp] * pitch;
+        double acc = 0.0;
+        for (int pc = 0; pc < sm.npieces; ++pc) acc += wrow[sm.piece[pc].slabcol] * sm.dots[pc * m3 + qrs];
+        ll_store(pslot + 2 * (size_t)en, (unsigned long long)__double_as_longlong(acc), ptag);
+    };
+    const bool single = sm.ncd <= TILE_LEN;
+    const bool tm2 = (widx == 0 && tid == DOT_THREADS);
+    unsigned long long t_b2 = tm2 ? gtimer() : 0;
+    if (single) {
+        tile_pass(0, sm.ncd);
+        __syncthreads();
+        if (tm2) {
+            const unsigned long long t = gtimer();
+            sm.t_pass += t - t_b2;
+            t_b2 = t;
+        }
+        if (m > 0) {
+            // four lanes per dot product (columns d = part mod 4), two shuffles, then the entries: all threads take part
+            auto dots_quads = [&](auto mc) {
+                constexpr int M = decltype(mc)::value, M3 = M * M * M;
+                for (int base = 0; base < ndot * 4; base += THREADS) {
+                    const int idx4 = base + tid, idx = idx4 >> 2, part = idx4 & 3;
+                    double acc = 0.0;
+                    if (idx < ndot) {
+                        const int pc = idx / M3, qrs = idx - pc * M3, qr = qrs / M, ss = qrs - qr * M, q = qr / M, r = qr - q * M;
+                        const int lo = sm.piece[pc].col0, hi = lo + sm.piece[pc].len;
+                        const double *row = sm.tile + (sm.st.tpos[q] * e + sm.st.tpos[r]) * TILE_PITCH;
+                        const double *wrow = Wr + (size_t)sm.st.tpos[ss] * pitch;
+                        double a0 = 0.0, a1 = 0.0;
+                        int d = lo + part;
+                        for (; d + 4 < hi; d += 8) {
+                            a0 += row[d] * wrow[d];
+                            a1 += row[d + 4] * wrow[d + 4];
+                        }
+                        if (d < hi) a0 += row[d] * wrow[d];
+                        acc = a0 + a1;
+                    }
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                    if (part == 0 && idx < ndot) sm.dots[idx] = acc;
+                }
+                __syncthreads();
+                for (int en = tid; en < M * M3; en += THREADS) {
+                    const int pp = en / M3, qrs = en - pp * M3;
+                    const double *wrow = Wr + (size_t)sm.st.tpos[pp] * pitch;
+                    double acc = 0.0;
+                    for (int pc = 0; pc < sm.npieces; ++pc) acc += wrow[sm.piece[pc].slabcol] * sm.dots[pc * M3 + qrs];
+                    ll_store(pslot + 2 * (size_t)en, (unsigned long long)__double_as_longlong(acc), ptag);
+                }
+            };
+            switch (m) {
+                case 2: dots_quads(std::integral_constant<int, 2>{}); break;
+                case 3: dots_quads(std::integral_constant<int, 3>{}); break;
+                case 4: dots_quads(std::integral_constant<int, 4>{}); break;
+                case 5: dots_quads(std::integral_constant<int, 5>{}); break;
+                default: dots_quads(std::integral_constant<int, 6>{}); break;
+            }
+        }
+    } else {
+        double dacc[2] = {0.0, 0.0};                 // thread <-> dot (piece, q, r, s) = tid, tid + THREADS
+        for (int t0 = 0; t0 < sm.ncd; t0 += TILE_LEN) {
+            const int tl = min(TILE_LEN, sm.ncd - t0);
+            tile_pass(t0, tl);
+            if (m > 0) {
+                __syncthreads();
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (tid + h * THREADS < ndot) dacc[h] += tile_dot(tid + h * THREADS, t0, tl);
+                __syncthreads();        // the tile is overwritten by the next chunk
+            }
+        }
+        if (m > 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (tid + h * THREADS < ndot) sm.dots[tid + h * THREADS] = dacc[h];
+            __syncthreads();
+            for (int en = tid; en < m * m3; en += THREADS) post_entry(en);
+        }
+    }
+    if (widx == 0 && tid == 0) sm.t_tile += gtimer() - t_begin;
+
+    // ---- flat phase: every other row pair of rotation (i, j) inside the owned columns ----------------------------
+    if (rot) flat_update<V>(p.S, &sm, n, i, j, c, s, 0, 2LL * n * (sm.ncd / V), tid, THREADS);
+    if (tm2) sm.t_flat += gtimer() - t_b2;
+}
+
+// Warp 0 of a worker: the plan of step w (rotation w, super block w + LOOK); w < 0: the prologue super blocks
+// 0 .. LOOK-1 from the initial state (no rotation).  `myE` = this lane's entry of the previous step's E (or -1).
+__device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm, int w, int &myE) {
+    WorkerStep &st = sm.st;
+    const int lane = threadIdx.x;
+    if (myE >= 0) sm.skipmask[myE >> 5] = 0u;        // clear the skip bits of the previous step
+    int slot = w + LOOK;        // w = -3, -2, -1: super blocks 0, 1, 2 of the initial state
+    // everything that depends on the pair list only comes first: it overlaps the wait for the angle
+    int m = 0, Dq = -1;
+    if (slot < p.P) {
+        m = p.dtab[(size_t)slot * DT_STRIDE];
+        if (lane < MAXM) Dq = p.dtab[(size_t)slot * DT_STRIDE + 1 + lane];
+    } else {
+        slot = -1;
+    }
+    int i = 0, j = 0, acc = 0, alive = 1;
+    double c = 1.0, s = 0.0;
+    if (w >= 0) {
+        i = p.pairs[2 * w];
+        j = p.pairs[2 * w + 1];
+        if (lane == 0) {
+            const unsigned long long tw0 = gtimer();
+            alive = read_record(p, w, acc, c, s) ? 1 : 0;
+            sm.t_wait += gtimer() - tw0;
+        }
+        alive = __shfl_sync(0xffffffffu, alive, 0);
+        acc = __shfl_sync(0xffffffffu, acc, 0);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        s = __shfl_sync(0xffffffffu, s, 0);
+    }
+    __syncwarp();
+    // E = [i, j] (if rotated) + the orbitals of D other than i, j, in the order of D
+    const bool has = lane < m;
+    const bool isI = has && acc && Dq == i, isJ = has && acc && Dq == j, other = has && !isI && !isJ;
+    const unsigned om = __ballot_sync(0xffffffffu, other);
+    const int base = acc ? 2 : 0;
+    const int tpos = isI ? 0 : (isJ ? 1 : base + __popc(om & ((1u << lane) - 1u)));
+    const int e = base + __popc(om);
+    if (has) {
+        st.D[lane] = Dq;
+        st.tpos[lane] = tpos;
+        if (other) st.E[tpos] = Dq;
+    }
+    if (lane == 0) {
+        st.alive = alive;
+        st.rotated = acc;
+        st.i = i;
+        st.j = j;
+        st.c = c;
+        st.s = s;
+        st.m = m;
+        st.slot = slot;
+        st.e = e;
+        if (acc) {
+            st.E[0] = i;
+            st.E[1] = j;
+        }
+    }
+    __syncwarp();
+    myE = lane < e ? st.E[lane] : -1;
+    if (myE >= 0) atomicOr(&sm.skipmask[myE >> 5], 1u << (myE & 31));
+}
+
+__device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, double *Wr, int widx) {
+    double *Wg = p.wg + (size_t)widx * p.n * p.wc_cols;
+    const int tid = threadIdx.x, n = p.n;
+    // ---- owned columns: quanta [lo, hi) of the flat (slab, d / granule) space -------------------------------------
+    if (tid == 0) {
+        const long long qrow = n / p.granule, Q = (long long)p.na * qrow;
+        long long lo = Q * widx / p.nworkers, hi = Q * (widx + 1) / p.nworkers;
+        int np = 0, col = 0;
+        while (lo < hi && np < MAX_PIECES) {
+            const int slab = (int)(lo / qrow);
+            const long long end = min(hi, (long long)(slab + 1) * qrow);
+            Piece &pc = sm.piece[np++];
+            pc.slab = slab;
+            pc.d0 = (int)(lo - (long long)slab * qrow) * p.granule;
+            pc.len = (int)(end - lo) * p.granule;
+            pc.col0 = col;
+            pc.base = (long long)slab * n * n * n + pc.d0 - col;
+            col += pc.len;
+            lo = end;
+        }
+        sm.ncd = col;
+        for (int k = 0; k < np; ++k) sm.piece[k].slabcol = col++;
+        sm.npieces = np;
+        sm.ncols = col;
+    }
+    for (int k = tid; k < 128; k += THREADS) sm.skipmask[k] = 0u;
+    if (tid == 0) sm.t_tile = sm.t_wait = sm.t_pass = sm.t_flat = 0;
+    __syncthreads();
+    // this worker's columns of W into its private copy
+    for (int pc = 0; pc < sm.npieces; ++pc) {
+        const Piece P = sm.piece[pc];
+        for (int e = tid; e < n * P.len; e += THREADS) {
+            const int x = e / P.len, d = e - x * P.len;
+            Wg[(size_t)x * p.wc_cols + P.col0 + d] = __ldcg(p.W + (size_t)x * n + P.d0 + d);
+        }
+        for (int x = tid; x < n; x += THREADS) Wg[(size_t)x * p.wc_cols + P.slabcol] = __ldcg(p.W + (size_t)x * n + p.a0 + P.slab);
+    }
+    __syncthreads();
+    int myE = -1;
+    const bool timing = (widx == 0 && tid == 0);
+    unsigned long long t_plan = 0, t_step = 0, tq = timing ? gtimer() : 0;
+    for (int w = -LOOK; w < p.P; ++w) {
+        if (tid < 32) plan_worker_step(p, sm, w, myE);
+        __syncthreads();
+        if (!sm.st.alive) return;
+        if (timing) {
+            const unsigned long long t = gtimer();
+            t_plan += t - tq;
+            tq = t;
+        }
+        if (sm.st.rotated || sm.st.m > 0) {
+            if ((n & 1) == 0) worker_step<2>(p, sm, Wg, Wr, widx);
+            else worker_step<1>(p, sm, Wg, Wr, widx);
+        }
+        __syncthreads();
+        if (timing) {
+            const unsigned long long t = gtimer();
+            t_step += t - tq;
+            tq = t;
+        }
+    }
+    if (timing) {
+        p.summary[16] = (double)t_plan;       // waiting for the angle + planning
+        p.summary[17] = (double)t_step;       // tile phase + flat phase
+        p.summary[18] = (double)sm.t_tile;    // tile phase (incl. partial post) of worker 0
+        p.summary[19] = (double)sm.t_wait;    // of [16]: inside the wait for the angle record
+        p.summary[22] = (double)sm.t_pass;    // tile pass (global loads, rotation, stores) up to the CTA barrier, thread 128
+        p.summary[23] = (double)sm.t_flat;    // flat phase as seen by thread 128 (not a dot-product thread)
+    }
+}
+
+// =====================================================================================================================
+// CTAs 1..NRED: reduction of the partial super blocks (fixed order), publication of the total.  Reducer r owns the
+// entries [ne r / NRED, ne (r + 1) / NRED).
+// =====================================================================================================================
+__device__ __forceinline__ void reducer_main(const Params &p, double *scratch /* [8][SB_MAX] smem */, int *flag_sm, int ridx) {
+    const int tid = threadIdx.x;
+    unsigned long long t_wait = 0, t_red = 0, tq = gtimer();
+    if (tid == 0) flag_sm[0] = 0;
+    __syncthreads();
+    for (int k = 0; k < p.P; ++k) {
+        const int slot = k & (SLOTS - 1);
+        const int m = p.dtab[(size_t)k * DT_STRIDE];
+        const int ne = m * m * m * m, e_lo = ne * ridx / NRED, e_hi = ne * (ridx + 1) / NRED, nl = e_hi - e_lo;
+        // `ns` sub-sums per entry over interleaved subsets of the workers: every thread has 8 tagged loads in flight and
+        // re-polls a batch until all its tags are those of super block k
+        const int ns = nl > 0 ? max(1, min(8, THREADS / nl)) : 1;
+        const unsigned long long want = (p.launch_id << 32) | (unsigned long long)(k + 1);
+        const unsigned long long *pb = p.pbuf + (size_t)slot * p.nworkers * SB_MAX * 2;
+        bool ok = true;
+        for (int it = tid; it < nl * ns; it += THREADS) {
+            const int el = it % nl, sub = it / nl;
+            double a8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a8[u] = 0.0;
+            for (int w0 = sub; w0 < p.nworkers; w0 += 8 * ns) {
+                unsigned long long v[8], g[8];
+                ok &= spin_until(p, [&]() {
+                    bool all = true;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int wk = w0 + u * ns;
+                        if (wk < p.nworkers) ll_load(pb + ((size_t)wk * SB_MAX + e_lo + el) * 2, v[u], g[u]);
+                        else { v[u] = 0ull; g[u] = want; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) all &= (g[u] == want);
+                    return all;
+                });
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a8[u] += __longlong_as_double((long long)v[u]);
+            }
+#pragma unroll
+            for (int w = 4; w > 0; w >>= 1)
+#pragma unroll
+                for (int u = 0; u < w; ++u) a8[u] += a8[u + w];
+            scratch[sub * SB_MAX + el] = a8[0];
+        }
+        if (!ok) flag_sm[0] = -1;
+        if (tid == 0) {
+            const unsigned long long t = gtimer();
+            t_wait += t - tq;
+            tq = t;
+        }
+        __syncthreads();
+        if (flag_sm[0] < 0) return;
+        for (int el = tid; el < nl; el += THREADS) {
+            double total = scratch[el];
+            for (int sub = 1; sub < ns; ++sub) total += scratch[sub * SB_MAX + el];
+            const int e = e_lo + el;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
+            if (p.nranks > 1) {
+                const unsigned long long tag = (p.epoch << 32) | (unsigned long long)(k + 1);
+                for (int dst = 0; dst < p.nranks; ++dst) {
+                    unsigned long long *w = reinterpret_cast<unsigned long long *>(p.mailboxes[dst]) +
+                                            (((size_t)(k & (MB_SLOTS - 1)) * p.nranks + p.rank) * SB_MAX + e) * 2;
+                    ll_store(w, bits, tag);
+                }
+            } else {
+                ll_store(p.tot + ((size_t)slot * TOT_WORDS + e) * 2, bits, (unsigned long long)(k + 1));
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long t = gtimer();
+            t_red += t - tq;
+            tq = t;
+        }
+    }
+    if (ridx == 0 && tid == 0) {
+        p.summary[20] = (double)t_wait;       // reducer 0: waiting for the partials
+        p.summary[21] = (double)t_red;        // reducer 0: summing + publishing
+    }
+}
+
+// =====================================================================================================================
+// CTA NRED + 1: gamma, U, W (global) and the gamma part of the super blocks
+// =====================================================================================================================
+__device__ __forceinline__ void aux_main(const Params &p, int *flag_sm, double *cs_sm) {
+    const int tid = threadIdx.x, n = p.n;
+    const size_t ld = 2 * (size_t)n;
+    auto publish_gamma = [&](int k) {       // gamma entries of super block k from the current gamma
+        if (k >= p.P) return;
+        if (tid < 1 + MAXM) flag_sm[1 + tid] = p.dtab[(size_t)k * DT_STRIDE + tid];
+        __syncthreads();
+        const int m = flag_sm[1];
+        if (tid < 2 * m * m) {
+            const int spin = tid / (m * m), r = tid - spin * m * m, pp = r / m, qq = r - pp * m;
+            const double v = __ldcg(p.gamma + (2 * (size_t)flag_sm[2 + pp] + spin) * ld + 2 * flag_sm[2 + qq] + spin);
+            ll_store(p.tot + ((size_t)(k & (SLOTS - 1)) * TOT_WORDS + SB_MAX + tid) * 2,
+                     (unsigned long long)__double_as_longlong(v), (unsigned long long)(k + 1));
+        }
+        __syncthreads();
+    };
+    for (int b = 0; b < LOOK; ++b) publish_gamma(b);
+    for (int w = 0; w < p.P; ++w) {
+        if (tid == 0) {
+            int acc;
+            double c, s;
+            const bool ok = read_record(p, w, acc, c, s);
+            flag_sm[0] = ok ? acc : -1;
+            cs_sm[0] = c;
+            cs_sm[1] = s;
+        }
+        __syncthreads();
+        const int acc = flag_sm[0];
+        if (acc < 0) return;
+        const double c = cs_sm[0], s = cs_sm[1];
+        const int i = p.pairs[2 * w], j = p.pairs[2 * w + 1];
+        if (acc) {
+            // gamma <- V gamma V^T on the same-spin blocks: columns, then rows;  U <- V U;  W <- V W
+            for (int k = tid; k < 2 * n; k += THREADS) {
+                const int a = k >> 1, spin = k & 1;
+                double *row = p.gamma + (2 * (size_t)a + spin) * ld;
+                const double x = __ldcg(row + 2 * i + spin), y = __ldcg(row + 2 * j + spin);
+                row[2 * i + spin] = c * x + s * y;
+                row[2 * j + spin] = c * y - s * x;
+            }
+            for (int k = tid; k < n; k += THREADS) {
+                double *ui = p.U + (size_t)i * n + k, *uj = p.U + (size_t)j * n + k;
+                const double x = __ldcg(ui), y = __ldcg(uj);
+                *ui = c * x + s * y;
+                *uj = c * y - s * x;
+                double *wi = p.W + (size_t)i * n + k, *wj = p.W + (size_t)j * n + k;
+                const double x2 = __ldcg(wi), y2 = __ldcg(wj);
+                *wi = c * x2 + s * y2;
+                *wj = c * y2 - s * x2;
+            }
+            __syncthreads();
+            for (int k = tid; k < 2 * n; k += THREADS) {
+                const int b = k >> 1, spin = k & 1;
+                double *gi = p.gamma + (2 * (size_t)i + spin) * ld + 2 * b + spin, *gj = p.gamma + (2 * (size_t)j + spin) * ld + 2 * b + spin;
+                const double x = __ldcg(gi), y = __ldcg(gj);
+                *gi = c * x + s * y;
+                *gj = c * y - s * x;
+            }
+            __syncthreads();
+        }
+        publish_gamma(w + LOOK);
+    }
+}
+
+// =====================================================================================================================
+// CTA 0: prefetch (warps 10..15) and search (warps 0..9)
+// =====================================================================================================================
+struct SearchSmem {
+    LineSearchSmemT<SEARCH_THREADS> ls;
+    double sb[2][TOT_WORDS];        // double-buffered super block (+ gamma part) of the pair being / to be searched
+    int sb_ok[2];
+    double y1[2 * MAXM * MAXM * MAXM];   // contraction scratch
+    double y2[4 * MAXM * MAXM];
+    double y3[8 * MAXM];
+    double blk[QIO_B200_BLOCK_DOUBLES];
+    double T[2 * MAXM];
+    PairCoef pc;
+    double2 coarse_cs[320];
+    int32_t fine_len[320];
+    int meta[2][12];                // per buffer: m, pos(i), pos(j), inactive(i), inactive(j), pa0, pb0, pa1, pb1 (-1: none)
+    int fetch_abort;
+};
+
+// named barriers: 1 = line search (320), 2 + b = full[b], 4 + b = empty[b] (512: one side arrives, the other syncs),
+// 6 = prefetch warps among themselves (192)
+__device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
+    const int ft = threadIdx.x - SEARCH_THREADS;
+    for (int k = 0; k < p.P; ++k) {
+        const int b = k & 1;
+        if (k >= 2) named_sync_id<THREADS>(4 + b);          // buffer b has been consumed (pair k - 2)
+        const int32_t *dt = p.dtab + (size_t)k * DT_STRIDE;
+        const int m_k = dt[0];
+        const int ne = m_k * m_k * m_k * m_k, ng = 2 * m_k * m_k;
+        if (ft < 9) {       // meta: m, pos(i), pos(j), inactive(i), inactive(j), pa0, pb0, pa1, pb1
+            const int src = ft == 0 ? 0 : (ft <= 2 ? 6 + ft : (ft <= 4 ? 10 + ft : 4 + ft));
+            sm.meta[b][ft] = dt[src];
+        }
+        bool ok = true;
+        for (int e = ft; e < ne + ng; e += FETCH_THREADS) {
+            const bool is_g = e >= ne;
+            const int word = is_g ? SB_MAX + (e - ne) : e;
+            double acc = 0.0;
+            if (p.nranks > 1 && !is_g) {
+                const unsigned long long tag = (p.epoch << 32) | (unsigned long long)(k + 1);
+                for (int r = 0; r < p.nranks; ++r) {
+                    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(p.mailboxes[p.rank]) +
+                                                  (((size_t)(k & (MB_SLOTS - 1)) * p.nranks + r) * SB_MAX + e) * 2;
+                    unsigned long long v = 0, g = 0;
+                    ok &= spin_until(p, [&]() {
+                        ll_load(w, v, g);
+                        return g == tag;
+                    });
+                    acc += __longlong_as_double((long long)v);
+                }
+            } else {
+                const unsigned long long *w = p.tot + ((size_t)(k & (SLOTS - 1)) * TOT_WORDS + word) * 2;
+                unsigned long long v = 0, g = 0;
+                ok &= spin_until(p, [&]() {
+                    ll_load(w, v, g);
+                    return g == (unsigned long long)(k + 1);
+                });
+                acc = __longlong_as_double((long long)v);
+            }
+            sm.sb[b][word] = acc;
+        }
+        if (!ok) sm.fetch_abort = 1;
+        named_sync<6, FETCH_THREADS>();
+        if (ft == 0) sm.sb_ok[b] = sm.fetch_abort ? 0 : 1;
+        __threadfence_block();
+        named_arrive_id<THREADS>(2 + b);                    // full[b]
+        if (sm.fetch_abort) {
+            // keep the barrier protocol matched: the searcher leaves after seeing sb_ok = 0 and arrives nowhere else
+            return;
+        }
+    }
+}
+
+__device__ __forceinline__ void search_main(const Params &p, SearchSmem &sm) {
+    const int tid = threadIdx.x;
+    ThetaTablesDev tab = p.tab;
+    if (tab.n_coarse <= 320) {
+        for (int t = tid; t < tab.n_coarse; t += SEARCH_THREADS) {
+            sm.coarse_cs[t] = reinterpret_cast<const double2 *>(tab.coarse_cs)[t];
+            sm.fine_len[t] = tab.fine_len[t];
+        }
+        tab.coarse_cs = reinterpret_cast<const double *>(sm.coarse_cs);
+        tab.fine_len = sm.fine_len;
+    }
+    if (tid < 8) sm.ls.prof[tid] = 0;
+    int accepted_total = 0, flags_or = 0;
+    // the last LOOK - 1 = 2 angles (accepted, c, s), newest last
+    int h_acc[2] = {0, 0};
+    double h_c[2] = {1.0, 1.0}, h_s[2] = {0.0, 0.0};
+    unsigned long long t_wait = 0, t_setup = 0, t_search = 0, t_pub = 0, tq = gtimer();
+    bool alive = true;
+    for (int k = 0; k < p.P && alive; ++k) {
+        const int b = k & 1;
+        named_sync_id<THREADS>(2 + b);                      // full[b]: super block k is in sm.sb[b]
+        if (!sm.sb_ok[b]) {
+            alive = false;
+            break;
+        }
+        if (tid == 0) {
+            const unsigned long long t = gtimer();
+            t_wait += t - tq;
+            tq = t;
+        }
+        const int *mt = sm.meta[b];
+        const bool i_in = mt[3] != 0, j_in = mt[4] != 0;
+        if (tid < 2 * MAXM) {
+            // T[target][col] = (G1 G0)[x, col]: the target orbital x (i or j of pair k) after the pending rotations
+            // G0 (pair k-2) and G1 (pair k-1), in terms of the orbitals D before them.  G(v)[y, col] has <= 2 non-zeros.
+            const int tg = tid / MAXM, col = tid - tg * MAXM, x = mt[1 + tg];
+            auto G = [&](int h, int y, int cc) -> double {      // entry (y, cc) of rotation h (identity if not accepted)
+                const int pa = mt[5 + 2 * h], pb = mt[6 + 2 * h];
+                if (!h_acc[h] || pa < 0) return y == cc ? 1.0 : 0.0;
+                if (y == pa) return cc == pa ? h_c[h] : (cc == pb ? h_s[h] : 0.0);
+                if (y == pb) return cc == pa ? -h_s[h] : (cc == pb ? h_c[h] : 0.0);
+                return y == cc ? 1.0 : 0.0;
+            };
+            double val = 0.0;
+            if (col < mt[0]) {
+                const int pa1 = mt[7], pb1 = mt[8];
+                if (h_acc[1] && pa1 >= 0 && (x == pa1 || x == pb1)) val = G(1, x, pa1) * G(0, pa1, col) + G(1, x, pb1) * G(0, pb1, col);
+                else val = G(0, x, col);
+            }
+            sm.T[tid] = val;
+        }
+        const int m_k = mt[0];
+        ls_sync<SEARCH_THREADS>();
+        {   // B = T^(x4) P_k: contract s, r, q, p in turn
+            const int m = m_k, m2 = m * m, m3 = m2 * m;
+            const double *sb = sm.sb[b], *T = sm.T;
+            for (int o = tid; o < 2 * m3; o += SEARCH_THREADS) {           // y1[pqr][de]
+                const int de = o & 1, pqr = o >> 1;
+                double acc = 0.0;
+                for (int s = 0; s < m; ++s) acc += T[de * MAXM + s] * sb[pqr * m + s];
+                sm.y1[o] = acc;
+            }
+            // gamma entries: spin, al, be
+            if (tid >= SEARCH_THREADS - 8) {
+                const int u = tid - (SEARCH_THREADS - 8), spin = u >> 2, al = (u >> 1) & 1, be = u & 1;
+                double acc = 0.0;
+                for (int a = 0; a < m; ++a)
+                    for (int c2 = 0; c2 < m; ++c2) acc += T[al * MAXM + a] * T[be * MAXM + c2] * sb[SB_MAX + spin * m2 + a * m + c2];
+                sm.blk[16 + u] = acc;
+            }
+            ls_sync<SEARCH_THREADS>();
+            for (int o = tid; o < 4 * m2; o += SEARCH_THREADS) {           // y2[pq][ga][de]
+                const int de = o & 1, ga = (o >> 1) & 1, pq = o >> 2;
+                double acc = 0.0;
+                for (int r = 0; r < m; ++r) acc += T[ga * MAXM + r] * sm.y1[(pq * m + r) * 2 + de];
+                sm.y2[o] = acc;
+            }
+            ls_sync<SEARCH_THREADS>();
+            for (int o = tid; o < 8 * m; o += SEARCH_THREADS) {            // y3[p][be][ga][de]
+                const int gd = o & 3, be = (o >> 2) & 1, pp = o >> 3;
+                double acc = 0.0;
+                for (int q = 0; q < m; ++q) acc += T[be * MAXM + q] * sm.y2[(pp * m + q) * 4 + gd];
+                sm.y3[o] = acc;
+            }
+            ls_sync<SEARCH_THREADS>();
+            if (tid < 16) {
+                const int rest = tid & 7, al = tid >> 3;
+                double acc = 0.0;
+                for (int pp = 0; pp < m; ++pp) acc += T[al * MAXM + pp] * sm.y3[pp * 8 + rest];
+                sm.blk[tid] = acc;
+            }
+            ls_sync<SEARCH_THREADS>();
+            if (tid == 0) make_coef(sm.blk, sm.pc);
+            ls_sync<SEARCH_THREADS>();
+        }
+        named_arrive_id<THREADS>(4 + b);                    // empty[b]: the prefetch warps may overwrite sm.sb[b]
+        if (tid == 0) {
+            const unsigned long long t = gtimer();
+            t_setup += t - tq;
+            tq = t;
+        }
+        qio_b200_ls_result res;
+        cta_linesearch_t<SEARCH_THREADS, PairCoef>(sm.pc, i_in, j_in, tab, sm.ls, res);
+        if (tid == 0) {
+            const unsigned long long t = gtimer();
+            t_search += t - tq;
+            tq = t;
+            unsigned long long *w = p.ring + (size_t)(k & (RING - 1)) * 4;
+            const unsigned long long tag = 2ull * (unsigned long long)(k + 1) + (res.accepted ? 1ull : 0ull);
+            ll_store(w, (unsigned long long)__double_as_longlong(res.cos_theta), tag);
+            ll_store(w + 2, (unsigned long long)__double_as_longlong(res.sin_theta), tag);
+            p.results[k] = res;
+            const unsigned long long t2 = gtimer();
+            t_pub += t2 - tq;
+            tq = t2;
+        }
+        h_acc[0] = h_acc[1];
+        h_c[0] = h_c[1];
+        h_s[0] = h_s[1];
+        h_acc[1] = res.accepted;
+        h_c[1] = res.cos_theta;
+        h_s[1] = res.sin_theta;
+        accepted_total += res.accepted;
+        flags_or |= res.flags;
+    }
+    if (tid == 0) {
+        p.summary[0] = (double)accepted_total;
+        p.summary[2] = (double)flags_or;
+        p.summary[3] = alive ? 0.0 : 1.0;
+        p.summary[5] = (double)t_wait;        // waiting for the super block (prefetch not ready)
+        p.summary[6] = (double)t_search;      // line search
+        p.summary[7] = (double)t_pub;         // record + result stores
+        p.summary[8] = 0.0;
+        p.summary[9] = (double)t_setup;       // T, contraction, coefficients
+        for (int q = 0; q < 6; ++q) p.summary[10 + q] = (double)sm.ls.prof[q];
+        p.summary[24] = 3.0;                  // engine id
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) sweep3_kernel(Params p) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const int cta = blockIdx.x;
+    if (cta == 0) {
+        SearchSmem &sm = *reinterpret_cast<SearchSmem *>(dyn);
+        if (threadIdx.x == 0) sm.fetch_abort = 0;
+        __syncthreads();
+        if (threadIdx.x < SEARCH_THREADS) search_main(p, sm);
+        else fetch_main(p, sm);
+    } else if (cta <= NRED) {
+        double *scratch = reinterpret_cast<double *>(dyn);
+        int *flags = reinterpret_cast<int *>(scratch + 8 * SB_MAX);
+        reducer_main(p, scratch, flags, cta - 1);
+    } else if (cta == AUX_CTA) {
+        int *flags = reinterpret_cast<int *>(dyn);
+        double *cs = reinterpret_cast<double *>(dyn + 64);
+        aux_main(p, flags, cs);
+    } else {
+        const int widx = cta - FIRST_WORKER;
+        if (widx >= p.nworkers) return;
+        WorkerSmem &sm = *reinterpret_cast<WorkerSmem *>(dyn);
+        double *Wr = reinterpret_cast<double *>(dyn + ((sizeof(WorkerSmem) + 15) / 16) * 16);
+        worker_main(p, sm, Wr, widx);
+    }
+}
+
+struct Layout {
+    size_t off_ring, off_count, off_abort, off_tot, off_pbuf, off_dtab, off_wg, total;
+};
+static Layout ws_layout(int max_workers, int n) {
+    Layout L;
+    L.off_ring = 0;
+    L.off_count = L.off_ring + sizeof(unsigned long long) * RING * 4;
+    L.off_abort = L.off_count + 64;
+    L.off_tot = L.off_abort + 64;
+    L.off_pbuf = L.off_tot + sizeof(unsigned long long) * 2 * SLOTS * TOT_WORDS;
+    L.off_dtab = L.off_pbuf + sizeof(unsigned long long) * 2 * (size_t)SLOTS * max_workers * SB_MAX;
+    L.off_wg = L.off_dtab + sizeof(int32_t) * DT_STRIDE * ((size_t)n * (n - 1) / 2 + 1);
+    L.off_wg = (L.off_wg + 255) / 256 * 256;
+    // private W columns: every worker holds at most ceil(n^2 / workers') + MAX_PIECES columns (na <= n); bound with the
+    // smallest worker count that can occur (Q >= workers) -- n (n + MAX_PIECES + 4) columns in total cover every case
+    L.total = L.off_wg + sizeof(double) * (size_t)n * ((size_t)n * n + (size_t)max_workers * (MAX_PIECES + 8));
+    return L;
+}
+
+}  // namespace s3
+
+size_t sweep3_workspace_bytes(int n) { return s3::ws_layout(sm_count(), n).total; }
+size_t sweep3_mailbox_bytes(int nranks) {
+    return sizeof(unsigned long long) * 2 * (size_t)s3::MB_SLOTS * (size_t)(nranks > 0 ? nranks : 1) * s3::SB_MAX;
+}
+
+// Shared memory of a worker for this problem, or 0 if the pipelined kernel cannot take it.
+static size_t worker_smem_bytes(int n, int na, int grid, int &nworkers, int &granule, int &wc_cols) {
+    using namespace s3;
+    if (grid < FIRST_WORKER + 1 || n > 4096 || na < 1) return 0;
+    granule = (n % 4 == 0) ? 4 : ((n % 2 == 0) ? 2 : 1);
+    const long long qrow = n / granule, Q = (long long)na * qrow;
+    nworkers = (int)std::min<long long>(grid - FIRST_WORKER, Q);
+    // the longest owned range, and the most pieces it can break into
+    const long long per = (Q + nworkers - 1) / nworkers;
+    const long long pieces = (per + qrow - 1) / qrow + 1;
+    if (pieces > MAX_PIECES) return 0;
+    wc_cols = (int)(per * granule + pieces);
+    wc_cols += (wc_cols & 1);      // even pitch
+    return ((sizeof(WorkerSmem) + 15) / 16) * 16 + sizeof(double) * (size_t)MAXE * wc_cols;
+}
+
+bool sweep3_supported(int n, int na) {
+    int nw, g, cols;
+    const size_t b = worker_smem_bytes(n, na, sm_count(), nw, g, cols);
+    return b > 0 && b <= 200 * 1024;
+}
+
+int sweep3_launch(double *gamma, double *S, double *U, double *W, int n, int a0, int na, const int32_t *pairs, int P,
+                  const int32_t *inactive, const qio_b200_theta_tables *h_tables, qio_b200_ls_result *results,
+                  double *summary, void *workspace, const qio_b200_peers *h_peers, cudaStream_t st) {
+    using namespace s3;
+    const int grid = sm_count();
+    Params p;
+    const size_t wsm = worker_smem_bytes(n, na, grid, p.nworkers, p.granule, p.wc_cols);
+    QIO_REQUIRE(wsm > 0 && wsm <= 200 * 1024, "sweep_cycle: problem does not fit the pipelined kernel");
+    const Layout L = ws_layout(grid, n);
+    QIO_REQUIRE((long long)P <= (long long)n * (n - 1) / 2 + 1, "sweep_cycle: more pairs than n (n - 1) / 2 (pipelined kernel)");
+    char *ws = reinterpret_cast<char *>(workspace);
+    QIO_CUDA(cudaMemsetAsync(ws, 0, L.off_pbuf, st));
+    QIO_CUDA(cudaMemsetAsync(summary, 0, 32 * sizeof(double), st));
+    p.S = S;
+    p.gamma = gamma;
+    p.U = U;
+    p.W = W;
+    p.n = n;
+    p.a0 = a0;
+    p.na = na;
+    p.pairs = pairs;
+    p.P = P;
+    p.inactive = inactive;
+    p.tab = to_dev(*h_tables);
+    p.results = results;
+    p.summary = summary;
+    p.ring = reinterpret_cast<unsigned long long *>(ws + L.off_ring);
+    p.abort_flag = reinterpret_cast<unsigned *>(ws + L.off_abort);
+    p.tot = reinterpret_cast<unsigned long long *>(ws + L.off_tot);
+    p.pbuf = reinterpret_cast<unsigned long long *>(ws + L.off_pbuf);
+    static unsigned long long launch_counter = 0;
+    p.launch_id = ++launch_counter;
+    p.dtab = reinterpret_cast<const int32_t *>(ws + L.off_dtab);
+    p.wg = reinterpret_cast<double *>(ws + L.off_wg);
+    QIO_REQUIRE(L.off_wg + sizeof(double) * (size_t)p.nworkers * n * p.wc_cols <= L.total, "sweep_cycle: workspace too small for the private W columns");
+    p.rank = h_peers ? h_peers->rank : 0;
+    p.nranks = h_peers ? h_peers->nranks : 1;
+    p.epoch = h_peers ? (unsigned long long)h_peers->epoch : 0ull;
+    p.mailboxes = p.nranks > 1 ? reinterpret_cast<double *const *>(h_peers->mailboxes) : nullptr;
+    size_t dyn = std::max(wsm, sizeof(SearchSmem));
+    dyn = std::max(dyn, sizeof(double) * 8 * SB_MAX + 256);
+    QIO_CUDA(cudaFuncSetAttribute(sweep3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    int blocks_per_sm = 0;
+    QIO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sweep3_kernel, THREADS, dyn));
+    QIO_REQUIRE(blocks_per_sm >= 1, "sweep_cycle: pipelined kernel does not fit on an SM");
+    if (P > 0) {
+        build_dtab_kernel<<<(P + 127) / 128, 128, 0, st>>>(pairs, inactive, P, reinterpret_cast<int32_t *>(ws + L.off_dtab));
+        QIO_LAUNCH_CHECK();
+        void *args[] = {&p};
+        QIO_CUDA(cudaLaunchCooperativeKernel((const void *)sweep3_kernel, dim3(grid), dim3(THREADS), args, dyn, st));
+    }
+    return QIO_B200_OK;
+}
+
+}  // namespace qio

@@ -229,6 +229,16 @@ def sweep_cycle(gamma, S, U, W, n, pairs, mask, tables, a0=0, na=None, peers=Non
     return results[:P * LS_DTYPE.itemsize], summary
 
 
+def sweep_engine(n, na=None):
+    return int(lib.qio_b200_sweep_engine(n, n if na is None else na))
+
+
+def check_sweep_summary(summary_host):
+    """Raises if the pipelined sweep kernel reported a timed-out wait (summary[3])."""
+    if float(summary_host[3]) != 0.0:
+        raise QioCudaError('sweep_cycle: a wait inside the pipelined kernel timed out; the cycle is incomplete')
+
+
 def deferred_diagonals(gamma, S, W, n, inds, a0=0, na=None):
     na = n if na is None else na
     m = int(inds.numel())

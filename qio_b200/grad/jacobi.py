@@ -133,7 +133,9 @@ class SweepState:
             diag = dev.deferred_diagonals(self.g, self.G, self.W, n, self.inds)
             _, _, _, esum = dev.orbital_entropies(diag, want_spec=False)
             dev.zero_offspin_if_rotated(self.g, n, summary)
-            n_acc, _, flags = dev.to_host(summary)[:3]
+            summ_h = dev.to_host(summary)
+            dev.check_sweep_summary(summ_h)
+            n_acc, _, flags = summ_h[:3]
             cost, _, _, eflags = dev.to_host(esum)
             flags = int(flags) | int(eflags)
         else:

@@ -235,7 +235,9 @@ class ShardedRDM:
         allreduce_sum_(diag, self.group)
         _, _, _, esum = dev.orbital_entropies(diag, want_spec=False)
         dev.zero_offspin_if_rotated(self.gamma, n, summary)
-        n_acc, _, flags = dev.to_host(summary)[:3]
+        summ_h = dev.to_host(summary)
+        dev.check_sweep_summary(summ_h)
+        n_acc, _, flags = summ_h[:3]
         cost, _, _, eflags = dev.to_host(esum)
         return dev.results_to_numpy(results), int(n_acc), float(cost), int(flags) | int(eflags)
 
