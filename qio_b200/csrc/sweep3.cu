@@ -52,7 +52,8 @@ constexpr int MAX_PIECES = 4;
 constexpr int TILE_LEN = 96;     // owned columns handled per super-block tile
 constexpr int TILE_PITCH = 98;   // row pitch of the tile: 196 words = 4 mod 32, the 8 rows a warp reads fall on different banks
 constexpr int DT_STRIDE = 16;     // ints per entry of the per-pair table
-constexpr int DOT_THREADS = 128;  // threads of a worker that finish the super block while the others stream the update
+constexpr int WORK_THREADS = THREADS - 32;   // a worker's warps 0..14 compute, warp 15 plans the next step (polls the angle)
+constexpr int TILE_THREADS = WORK_THREADS;   // all working warps do the tile phase, then the flat phase
 constexpr int NRED = 4;          // reducer CTAs (each sums a quarter of the entries)
 constexpr unsigned long long TIMEOUT_NS = 4000000000ull;
 constexpr int AUX_CTA = NRED + 1;
@@ -229,9 +230,9 @@ struct WorkerStep {             // built by thread 0 of a worker for each step, 
 struct WorkerSmem {
     Piece piece[MAX_PIECES];
     int npieces, ncols, ncd;    // ncd = owned d-columns (concatenated over the pieces); ncols = ncd + npieces
-    WorkerStep st;
+    WorkerStep st[2];           // double-buffered: the planner warp writes step w + 1 while step w runs
     unsigned long long t_tile, t_wait, t_pass, t_flat;
-    unsigned skipmask[128];     // bit x: rows with index x are handled by the tile phase of this step (n <= 4096)
+    unsigned skipmask[2][128];  // bit x: rows with index x are handled by the tile phase of that step (n <= 4096)
     double dots[MAX_PIECES * MAXM * MAXM * MAXM];       // [piece][q][r][s]
     alignas(16) double tile[MAXE * MAXE * TILE_PITCH];
 };
@@ -249,8 +250,8 @@ __device__ __forceinline__ int piece_of(const WorkerSmem &sm, int cc) {
 // bit is set in `skipmask` belong to the tile phase.  A separate function on purpose: its loop wants a clean register file
 // (four butterflies = eight independent 16-byte loads in flight per thread).
 template <int V>
-static __device__ __noinline__ void flat_update(double *__restrict__ S, const WorkerSmem *smp, int n, int i, int j, double c,
-                                                double s, long long first, long long last, int t, int nt) {
+static __device__ __noinline__ void flat_update(double *__restrict__ S, const WorkerSmem *smp, const unsigned *skipmask, int n, int i,
+                                                int j, double c, double s, long long first, long long last, int t, int nt) {
     using VT = typename std::conditional<V == 2, double2, double>::type;
     constexpr int UNR = 4;
     const WorkerSmem &sm = *smp;
@@ -270,7 +271,7 @@ static __device__ __noinline__ void flat_update(double *__restrict__ S, const Wo
         for (int u = 0; u < UNR; ++u) {
             const bool in = item < last;
             const int axis = rho2 >= n ? 1 : 0, xx = in ? rho2 - axis * n : 0;
-            const bool skip = !in || ((sm.skipmask[xx >> 5] >> (xx & 31)) & 1u);
+            const bool skip = !in || ((skipmask[xx >> 5] >> (xx & 31)) & 1u);
             const int cc = v * V;
             const long long pb = cc >= c3 ? b3 : (cc >= c2 ? b2 : (cc >= c1 ? b1 : b0));
             // bit 62 of the offset carries the axis
@@ -313,12 +314,12 @@ static __device__ __noinline__ void flat_update(double *__restrict__ S, const Wo
 // (if any) on the way.  Wg = the owned columns of W (private global copy, rotated here as well); Wr = shared-memory cache of
 // its rows E (the only ones a step reads), row t <-> orbital E[t].
 template <int V>
-__device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, double *Wg, double *Wr, int widx) {
+__device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, double *Wg, double *Wr, int widx, int buf) {
     using VT = typename std::conditional<V == 2, double2, double>::type;
     const int tid = threadIdx.x;
     const int n = p.n;
     const long long n1 = n, n2 = n1 * n1;
-    const WorkerStep &st = sm.st;
+    const WorkerStep &st = sm.st[buf];
     const bool rot = st.rotated != 0;
     const double c = st.c, s = st.s;
     const int i = st.i, j = st.j, m = st.m, e = st.e, pitch = p.wc_cols;
@@ -336,26 +337,50 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
         }
     };
 
-    // ---- W columns: rows E into shared memory, rows i, j rotated on the way (and written back) -----------------
-    // (these loads share the latency window of the tile pass below; the barrier after the tile pass covers them)
-    {
-        const int f0 = rot ? 2 : 0;
-        if (rot)
-            for (int col = tid; col < sm.ncols; col += THREADS) {
-                double *gi = Wg + (size_t)i * pitch + col, *gj = Wg + (size_t)j * pitch + col;
-                const double x = __ldcg(gi), y = __ldcg(gj);
-                const double xn = c * x + s * y, yn = c * y - s * x;
-                *gi = xn;
-                *gj = yn;
-                Wr[col] = xn;
-                Wr[pitch + col] = yn;
-            }
-        if (m > 0)
-            for (int idx = tid; idx < (e - f0) * sm.ncols; idx += THREADS) {
-                const int t = f0 + idx / sm.ncols, col = idx - (t - f0) * sm.ncols;
-                Wr[(size_t)t * pitch + col] = __ldcg(Wg + (size_t)sm.st.E[t] * pitch + col);
-            }
+    // ---- W columns: rows E into shared memory, rows i, j rotated on the way (and written back).  The loads are issued
+    // here and consumed after the tile pass has issued its own: one latency window for both.
+    const int f0 = rot ? 2 : 0, nother = m > 0 ? (e - f0) * sm.ncols : 0;
+    constexpr int WPRE = 4;
+    double wx = 0.0, wy = 0.0, wv[WPRE];
+    const bool wrot = rot && tid < sm.ncols;
+    if (wrot) {
+        wx = __ldcg(Wg + (size_t)i * pitch + tid);
+        wy = __ldcg(Wg + (size_t)j * pitch + tid);
     }
+#pragma unroll
+    for (int k = 0; k < WPRE; ++k) {
+        const int idx = tid + k * TILE_THREADS;
+        wv[k] = 0.0;
+        if (idx < nother) {
+            const int t = f0 + idx / sm.ncols, col = idx - (t - f0) * sm.ncols;
+            wv[k] = __ldcg(Wg + (size_t)st.E[t] * pitch + col);
+        }
+    }
+    auto w_consume = [&]() {
+        auto rot_col = [&](int col, double x, double y) {
+            const double xn = c * x + s * y, yn = c * y - s * x;
+            Wg[(size_t)i * pitch + col] = xn;
+            Wg[(size_t)j * pitch + col] = yn;
+            Wr[col] = xn;
+            Wr[pitch + col] = yn;
+        };
+        if (wrot) rot_col(tid, wx, wy);
+        if (rot)
+            for (int col = tid + TILE_THREADS; col < sm.ncols; col += TILE_THREADS)
+                rot_col(col, __ldcg(Wg + (size_t)i * pitch + col), __ldcg(Wg + (size_t)j * pitch + col));
+#pragma unroll
+        for (int k = 0; k < WPRE; ++k) {
+            const int idx = tid + k * TILE_THREADS;
+            if (idx < nother) {
+                const int t = f0 + idx / sm.ncols, col = idx - (t - f0) * sm.ncols;
+                Wr[(size_t)t * pitch + col] = wv[k];
+            }
+        }
+        for (int idx = tid + WPRE * TILE_THREADS; idx < nother; idx += TILE_THREADS) {
+            const int t = f0 + idx / sm.ncols, col = idx - (t - f0) * sm.ncols;
+            Wr[(size_t)t * pitch + col] = __ldcg(Wg + (size_t)st.E[t] * pitch + col);
+        }
+    };
 
     // ---- tile phase: the rows (x, y), x, y in E, of all owned columns ------------------------------------------
     // orbits of the rotation inside E x E: X = {IJ} + F (rotated) or X = E (not rotated); an orbit has 1, 2 or 4 rows
@@ -365,12 +390,12 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
     unsigned long long *pslot = p.pbuf + ((size_t)(st.slot & (SLOTS - 1)) * p.nworkers + widx) * SB_MAX * 2;
     auto tile_pass = [&](int t0, int tl) {
         const int tv = tl / V, nitems = nx * nx * tv;
-        for (int item = tid; item < nitems; item += THREADS) {
+        for (int item = tid; item < nitems; item += TILE_THREADS) {
             const int orb = item / tv, v = item - orb * tv;
             const int x1 = orb / nx, x2 = orb - x1 * nx;
             const bool two1 = rot && x1 == 0, two2 = rot && x2 == 0;
             const int ea0 = rot ? (x1 == 0 ? 0 : x1 + 1) : x1, eb0 = rot ? (x2 == 0 ? 0 : x2 + 1) : x2;   // E positions
-            const int oa0 = sm.st.E[ea0], ob0 = sm.st.E[eb0];
+            const int oa0 = st.E[ea0], ob0 = st.E[eb0];
             const int cc = t0 + v * V;
             double *g = p.S + sm.piece[piece_of(sm, cc)].base + cc + oa0 * n2 + ob0 * n1;
             const long long dj1 = (long long)(j - oa0) * n2, dj2 = (long long)(j - ob0) * n1;   // to the partner rows
@@ -411,8 +436,8 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
         const int pc = idx / m3, qrs = idx - pc * m3, qr = qrs / m, ss = qrs - qr * m, q = qr / m, r = qr - q * m;
         const Piece P = sm.piece[pc];
         const int lo = max(P.col0, t0), hi = min(P.col0 + P.len, t0 + tl);
-        const double *row = sm.tile + (sm.st.tpos[q] * e + sm.st.tpos[r]) * TILE_PITCH - t0;
-        const double *wrow = Wr + (size_t)sm.st.tpos[ss] * pitch;
+        const double *row = sm.tile + (st.tpos[q] * e + st.tpos[r]) * TILE_PITCH - t0;
+        const double *wrow = Wr + (size_t)st.tpos[ss] * pitch;
         double a0 = 0.0, a1 = 0.0;
         int d = lo;
         for (; d + 1 < hi; d += 2) {
@@ -425,17 +450,18 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
     // entry (p, q, r, s) = sum over the pieces of W[D_p, slab] * dot(piece, q, r, s), posted as a tagged 16-byte word
     auto post_entry = [&](int en) {
         const int pp = en / m3, qrs = en - pp * m3;
-        const double *wrow = Wr + (size_t)sm.st.tpos[pp] * pitch;
+        const double *wrow = Wr + (size_t)st.tpos[pp] * pitch;
         double acc = 0.0;
         for (int pc = 0; pc < sm.npieces; ++pc) acc += wrow[sm.piece[pc].slabcol] * sm.dots[pc * m3 + qrs];
         ll_store(pslot + 2 * (size_t)en, (unsigned long long)__double_as_longlong(acc), ptag);
     };
     const bool single = sm.ncd <= TILE_LEN;
-    const bool tm2 = (widx == 0 && tid == DOT_THREADS);
+    const bool tm2 = (widx == 0 && tid == 32);
     unsigned long long t_b2 = tm2 ? gtimer() : 0;
     if (single) {
         tile_pass(0, sm.ncd);
-        __syncthreads();
+        w_consume();
+        named_sync<2, TILE_THREADS>();
         if (tm2) {
             const unsigned long long t = gtimer();
             sm.t_pass += t - t_b2;
@@ -445,14 +471,14 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
             // four lanes per dot product (columns d = part mod 4), two shuffles, then the entries: all threads take part
             auto dots_quads = [&](auto mc) {
                 constexpr int M = decltype(mc)::value, M3 = M * M * M;
-                for (int base = 0; base < ndot * 4; base += THREADS) {
+                for (int base = 0; base < ndot * 4; base += TILE_THREADS) {
                     const int idx4 = base + tid, idx = idx4 >> 2, part = idx4 & 3;
                     double acc = 0.0;
                     if (idx < ndot) {
                         const int pc = idx / M3, qrs = idx - pc * M3, qr = qrs / M, ss = qrs - qr * M, q = qr / M, r = qr - q * M;
                         const int lo = sm.piece[pc].col0, hi = lo + sm.piece[pc].len;
-                        const double *row = sm.tile + (sm.st.tpos[q] * e + sm.st.tpos[r]) * TILE_PITCH;
-                        const double *wrow = Wr + (size_t)sm.st.tpos[ss] * pitch;
+                        const double *row = sm.tile + (st.tpos[q] * e + st.tpos[r]) * TILE_PITCH;
+                        const double *wrow = Wr + (size_t)st.tpos[ss] * pitch;
                         double a0 = 0.0, a1 = 0.0;
                         int d = lo + part;
                         for (; d + 4 < hi; d += 8) {
@@ -466,10 +492,10 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
                     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
                     if (part == 0 && idx < ndot) sm.dots[idx] = acc;
                 }
-                __syncthreads();
-                for (int en = tid; en < M * M3; en += THREADS) {
+                named_sync<2, TILE_THREADS>();
+                for (int en = tid; en < M * M3; en += TILE_THREADS) {
                     const int pp = en / M3, qrs = en - pp * M3;
-                    const double *wrow = Wr + (size_t)sm.st.tpos[pp] * pitch;
+                    const double *wrow = Wr + (size_t)st.tpos[pp] * pitch;
                     double acc = 0.0;
                     for (int pc = 0; pc < sm.npieces; ++pc) acc += wrow[sm.piece[pc].slabcol] * sm.dots[pc * M3 + qrs];
                     ll_store(pslot + 2 * (size_t)en, (unsigned long long)__double_as_longlong(acc), ptag);
@@ -488,35 +514,37 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
         for (int t0 = 0; t0 < sm.ncd; t0 += TILE_LEN) {
             const int tl = min(TILE_LEN, sm.ncd - t0);
             tile_pass(t0, tl);
+            if (t0 == 0) w_consume();
             if (m > 0) {
-                __syncthreads();
+                named_sync<2, TILE_THREADS>();
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
-                    if (tid + h * THREADS < ndot) dacc[h] += tile_dot(tid + h * THREADS, t0, tl);
-                __syncthreads();        // the tile is overwritten by the next chunk
+                    if (tid + h * TILE_THREADS < ndot) dacc[h] += tile_dot(tid + h * TILE_THREADS, t0, tl);
+                named_sync<2, TILE_THREADS>();        // the tile is overwritten by the next chunk
             }
         }
         if (m > 0) {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
-                if (tid + h * THREADS < ndot) sm.dots[tid + h * THREADS] = dacc[h];
-            __syncthreads();
-            for (int en = tid; en < m * m3; en += THREADS) post_entry(en);
+                if (tid + h * TILE_THREADS < ndot) sm.dots[tid + h * TILE_THREADS] = dacc[h];
+            named_sync<2, TILE_THREADS>();
+            for (int en = tid; en < m * m3; en += TILE_THREADS) post_entry(en);
         }
     }
     if (widx == 0 && tid == 0) sm.t_tile += gtimer() - t_begin;
 
     // ---- flat phase: every other row pair of rotation (i, j) inside the owned columns ----------------------------
-    if (rot) flat_update<V>(p.S, &sm, n, i, j, c, s, 0, 2LL * n * (sm.ncd / V), tid, THREADS);
+    if (rot) flat_update<V>(p.S, &sm, sm.skipmask[buf], n, i, j, c, s, 0, 2LL * n * (sm.ncd / V), tid, WORK_THREADS);
     if (tm2) sm.t_flat += gtimer() - t_b2;
 }
 
-// Warp 0 of a worker: the plan of step w (rotation w, super block w + LOOK); w < 0: the prologue super blocks
+// The planner warp of a worker: the plan of step w (rotation w, super block w + LOOK); w < 0: the prologue super blocks
 // 0 .. LOOK-1 from the initial state (no rotation).  `myE` = this lane's entry of the previous step's E (or -1).
-__device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm, int w, int &myE) {
-    WorkerStep &st = sm.st;
-    const int lane = threadIdx.x;
-    if (myE >= 0) sm.skipmask[myE >> 5] = 0u;        // clear the skip bits of the previous step
+__device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm, int w, int &myE, int buf) {
+    WorkerStep &st = sm.st[buf];
+    unsigned *skipmask = sm.skipmask[buf];
+    const int lane = threadIdx.x & 31;
+    if (myE >= 0) skipmask[myE >> 5] = 0u;        // clear the skip bits of the step that used this buffer before
     int slot = w + LOOK;        // w = -3, -2, -1: super blocks 0, 1, 2 of the initial state
     // everything that depends on the pair list only comes first: it overlaps the wait for the angle
     int m = 0, Dq = -1;
@@ -571,7 +599,7 @@ __device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm
     }
     __syncwarp();
     myE = lane < e ? st.E[lane] : -1;
-    if (myE >= 0) atomicOr(&sm.skipmask[myE >> 5], 1u << (myE & 31));
+    if (myE >= 0) atomicOr(&skipmask[myE >> 5], 1u << (myE & 31));
 }
 
 __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, double *Wr, int widx) {
@@ -599,7 +627,7 @@ __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, dou
         sm.npieces = np;
         sm.ncols = col;
     }
-    for (int k = tid; k < 128; k += THREADS) sm.skipmask[k] = 0u;
+    for (int k = tid; k < 256; k += THREADS) sm.skipmask[0][k] = 0u;
     if (tid == 0) sm.t_tile = sm.t_wait = sm.t_pass = sm.t_flat = 0;
     __syncthreads();
     // this worker's columns of W into its private copy
@@ -612,31 +640,35 @@ __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, dou
         for (int x = tid; x < n; x += THREADS) Wg[(size_t)x * p.wc_cols + P.slabcol] = __ldcg(p.W + (size_t)x * n + p.a0 + P.slab);
     }
     __syncthreads();
-    int myE = -1;
+    int myE[2] = {-1, -1};
     const bool timing = (widx == 0 && tid == 0);
+    const bool planner = tid >= WORK_THREADS;
     unsigned long long t_plan = 0, t_step = 0, tq = timing ? gtimer() : 0;
+    if (planner) plan_worker_step(p, sm, -LOOK, myE[0], 0);
+    __syncthreads();
     for (int w = -LOOK; w < p.P; ++w) {
-        if (tid < 32) plan_worker_step(p, sm, w, myE);
-        __syncthreads();
-        if (!sm.st.alive) return;
+        const int buf = (w + LOOK) & 1;
+        if (!sm.st[buf].alive) return;
         if (timing) {
             const unsigned long long t = gtimer();
             t_plan += t - tq;
             tq = t;
         }
-        if (sm.st.rotated || sm.st.m > 0) {
-            if ((n & 1) == 0) worker_step<2>(p, sm, Wg, Wr, widx);
-            else worker_step<1>(p, sm, Wg, Wr, widx);
+        if (planner) {
+            if (w + 1 < p.P) plan_worker_step(p, sm, w + 1, myE[buf ^ 1], buf ^ 1);     // overlaps step w
+        } else if (sm.st[buf].rotated || sm.st[buf].m > 0) {
+            if ((n & 1) == 0) worker_step<2>(p, sm, Wg, Wr, widx, buf);
+            else worker_step<1>(p, sm, Wg, Wr, widx, buf);
         }
-        __syncthreads();
         if (timing) {
             const unsigned long long t = gtimer();
             t_step += t - tq;
             tq = t;
         }
+        __syncthreads();
     }
     if (timing) {
-        p.summary[16] = (double)t_plan;       // waiting for the angle + planning
+        p.summary[16] = (double)t_plan;       // waiting at the step barrier (planner not ready / stragglers)
         p.summary[17] = (double)t_step;       // tile phase + flat phase
         p.summary[18] = (double)sm.t_tile;    // tile phase (incl. partial post) of worker 0
         p.summary[19] = (double)sm.t_wait;    // of [16]: inside the wait for the angle record
