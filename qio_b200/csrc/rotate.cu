@@ -14,9 +14,15 @@
 // Tiling: CTA = 128 (M) x 16*NT8 (N), 8 warps as 4 (M) x 2 (N), warp tile 32 x 8*NT8, K in slabs
 // of 16 through a 4-stage cp.async pipeline.  Shared-memory pitches (132 / 20 doubles) make all
 // fragment loads bank-conflict free.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace qio {
+
+// rotate_tma.cu: persistent TMA-fed kernel for MODE_CYCLIC / MODE_LEAD_KEEP; returns 1 if it ran, 0 if not eligible
+int rotate_axis_tma(const double *U, const double *in, double *out, int n, int kdim, long long ldu, long long rows,
+                    long long ld_in, long long ld_out, bool lead_keep, cudaStream_t st);
 
 constexpr int RA_BM = 128;
 constexpr int RA_BK = 16;
@@ -210,6 +216,14 @@ static int launch_rotate_axis(const double *U, const double *in, double *out, in
 template <int MODE>
 static int dispatch_rotate_axis(const double *U, const double *in, double *out, int n, int kdim, long long ldu,
                                 long long rows, long long ld_in, long long ld_out, cudaStream_t st) {
+    if (MODE != MODE_LAST) {
+        // QIO_B200_ROTATE=cpasync keeps the cp.async kernel of this file (A/B comparison)
+        const char *e = getenv("QIO_B200_ROTATE");
+        if (!(e && e[0] == 'c')) {
+            const int rc = rotate_axis_tma(U, in, out, n, kdim, ldu, rows, ld_in, ld_out, MODE == MODE_LEAD_KEEP, st);
+            if (rc != 0) return rc < 0 ? rc : QIO_B200_OK;
+        }
+    }
     // N tile = 16*NT8 columns: fewest padded columns, ties to the wider tile
     int best = 1;
     long long best_pad = -1;

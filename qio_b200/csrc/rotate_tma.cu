@@ -1,0 +1,249 @@
+// One axis of the 4-index rotation as a PERSISTENT, TMA-fed FP64 tensor-core GEMM (reference qio/grad/jacobi.py:90,
+// qio/grad/gradient.py:214: einsum 'ia,jb,kc,ld,abcd->ijkl', four single-axis passes).
+//
+//     C[M = rows, N = n] = A B,   A[m, k] = in[k * ld_in + m]  (K = kdim rows of M contiguous columns),   B[k, i] = U[i * ldu + k]
+//     MODE_CYCLIC:    out[m * n + i]       (the contracted leading axis re-appears as the last one)
+//     MODE_LEAD_KEEP: out[i * ld_out + m]  (order kept; the flush of the deferred sweep state)
+//
+// tcgen05.mma has no FP64 kind, so the tensor path is warp-level mma.sync m8n8k4 f64 (SASS DMMA.8x8x4) -- what this kernel
+// adds over rotate.cu is everything around it:
+//   * persistent: one CTA per SM loops over 128-row M tiles; the K slabs of consecutive tiles stream through one ring of
+//     shared-memory stages without ever draining the pipeline (a tile has only n / 8 = 13..25 slabs);
+//   * the A slabs come in by TMA (cp.async.bulk.tensor.3d, one instruction per 8 KB stage, issued by a producer warp and
+//     tracked by mbarriers); the tensor is described as [16][K][M / 16] so that one box = 8 k-rows x 128 m-columns lands as
+//     sixteen-double lines in SWIZZLE_128B order, and an MMA k-group takes the even (then the odd) rows of a slab: the
+//     fragment loads of a half-warp then hit all 32 banks exactly once.  Out-of-range rows / columns are zero-filled by
+//     the TMA unit, no predication in the kernel;
+//   * B (the rotation matrix, <= 104 columns per CTA) is resident in shared memory for the whole kernel, k-major with a
+//     pitch = 2 mod 16 doubles (conflict-free for the same k-groups);
+//   * the N tiles are split 7 + 6 between the two warp columns (warps w and w + 4 share a scheduler), so that n = 100 is
+//     padded to 104 columns instead of 112.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace qio {
+
+constexpr int RT_BM = 128;            // rows of an M tile
+constexpr int RT_KS = 8;              // k-rows per stage
+constexpr int RT_STAGE_DOUBLES = RT_KS * RT_BM;      // 8 KB
+constexpr int RT_CONSUMERS = 256;     // 8 warps: 4 (M) x 2 (N)
+constexpr int RT_THREADS = RT_CONSUMERS + 32;
+constexpr int RT_MAX_NT = 7;          // n8-tiles of the wider warp column
+constexpr int RT_MAX_COLS = 8 * (2 * RT_MAX_NT - 1);   // 104 columns per CTA
+constexpr int RT_MAX_STAGES = 8;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// grid = (CTAs along M (persistent), column blocks of <= 104);  dynamic shared memory:
+//   [stages][RT_STAGE_DOUBLES] A ring (1024-byte aligned) | Bs[kpad][np] | full[stages], empty[stages] mbarriers
+template <bool LEAD_KEEP>
+__global__ void __launch_bounds__(RT_THREADS, 1)
+    rotate_tma_kernel(const __grid_constant__ CUtensorMap tmA, const double *__restrict__ U, double *__restrict__ out, int n,
+                      int kdim, long long ldu, long long rows, long long ld_out, int cols_per_cta, int np, int kpad, int stages) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double *sA = reinterpret_cast<double *>(smem_raw);
+    double *sB = sA + (size_t)stages * RT_STAGE_DOUBLES;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(sB + (size_t)kpad * np);
+    unsigned long long *empty = full + RT_MAX_STAGES;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n0 = blockIdx.y * cols_per_cta, ncols = min(cols_per_cta, n - n0);
+    const int nslabs = kpad / RT_KS;
+    const long long mtiles = (rows + RT_BM - 1) / RT_BM;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, RT_CONSUMERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // B: sB[k][c] = U[n0 + c][k], zero beyond (kdim, ncols)
+    for (int e = tid; e < kpad * np; e += RT_THREADS) {
+        const int c = e / kpad, k = e - c * kpad;       // k fastest: coalesced reads of a row of U
+        if (c < np) sB[(size_t)k * np + c] = (c < ncols && k < kdim) ? U[(long long)(n0 + c) * ldu + k] : 0.0;
+    }
+    __syncthreads();
+
+    if (warp == RT_CONSUMERS / 32) {
+        // ---- producer warp: one lane streams the slabs of all tiles of this CTA through the ring -------------------
+        if (lane == 0) {
+            long long q = 0;
+            for (long long tile = blockIdx.x; tile < mtiles; tile += gridDim.x)
+                for (int ks = 0; ks < nslabs; ++ks, ++q) {
+                    const int s = (int)(q % stages);
+                    if (q >= stages) mbar_wait(empty + s, (unsigned)(((q / stages) - 1) & 1));
+                    mbar_expect_tx(full + s, RT_STAGE_DOUBLES * sizeof(double));
+                    tma_load_3d(sA + (size_t)s * RT_STAGE_DOUBLES, &tmA, 0, ks * RT_KS, (int)(tile * (RT_BM / 16)), full + s);
+                }
+        }
+        return;
+    }
+
+    // ---- consumers: 8 warps as 4 (M) x 2 (N) -------------------------------------------------------------------
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp & 3) * 32, wcol = warp >> 2;
+    const int tiles_n = (ncols + 7) / 8, nt_a = (tiles_n + 1) / 2;           // column 0: nt_a tiles, column 1: the rest
+    const int nt = wcol == 0 ? nt_a : tiles_n - nt_a, wn = wcol == 0 ? 0 : 8 * nt_a;
+    // per-lane constants of the swizzled A fragment: m = wm + 8 mi + g -> 16-double line chunk and position inside
+    int a_line[4], a_unit[4], a_low[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int mm = wm + 8 * mi + g;
+        a_line[mi] = (mm >> 4) * RT_KS;        // first line of that m-chunk
+        a_unit[mi] = (mm & 15) >> 1;
+        a_low[mi] = mm & 1;
+    }
+    long long q = 0;
+    for (long long tile = blockIdx.x; tile < mtiles; tile += gridDim.x) {
+        double acc[4][RT_MAX_NT][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < RT_MAX_NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int ks = 0; ks < nslabs; ++ks, ++q) {
+            const int s = (int)(q % stages);
+            mbar_wait(full + s, (unsigned)((q / stages) & 1));
+            const double *a = sA + (size_t)s * RT_STAGE_DOUBLES;
+            const double *b = sB + (size_t)(ks * RT_KS) * np + wn + g;
+#pragma unroll
+            for (int grp = 0; grp < 2; ++grp) {
+                const int r = 2 * t + grp;          // k-group: rows {0, 2, 4, 6} (+1) of the slab
+                double af[4], bf[RT_MAX_NT];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+                    af[mi] = a[(a_line[mi] + r) * 16 + ((a_unit[mi] ^ r) << 1) + a_low[mi]];
+#pragma unroll
+                for (int ni = 0; ni < RT_MAX_NT; ++ni) bf[ni] = ni < nt ? b[(size_t)r * np + 8 * ni] : 0.0;
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < RT_MAX_NT; ++ni)
+                        if (ni < nt) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+        }
+        // epilogue: C fragment (row g, cols 2t, 2t+1) of each 8x8 tile
+        const long long m0 = tile * RT_BM;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const long long m = m0 + wm + 8 * mi + g;
+            if (m >= rows) continue;
+#pragma unroll
+            for (int ni = 0; ni < RT_MAX_NT; ++ni) {
+                if (ni >= nt) continue;
+                const int col = n0 + wn + 8 * ni + 2 * t;
+                if (LEAD_KEEP) {
+                    if (col < n0 + ncols) out[(long long)col * ld_out + m] = acc[mi][ni][0];
+                    if (col + 1 < n0 + ncols) out[(long long)(col + 1) * ld_out + m] = acc[mi][ni][1];
+                } else {
+                    double *orow = out + m * ld_out;
+                    if (col + 1 < n0 + ncols) {
+                        *reinterpret_cast<double2 *>(orow + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                    } else if (col < n0 + ncols) {
+                        orow[col] = acc[mi][ni][0];
+                    }
+                }
+            }
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Returns 1 if the TMA kernel took the job, 0 if the shape is not eligible (the caller falls back to rotate.cu), < 0 on error.
+int rotate_axis_tma(const double *U, const double *in, double *out, int n, int kdim, long long ldu, long long rows,
+                    long long ld_in, long long ld_out, bool lead_keep, cudaStream_t st) {
+    if (rows % 16 != 0 || ld_in % 2 != 0 || ((uintptr_t)in % 16) != 0 || rows / 16 > 0x7fffffffLL || kdim < 1) return 0;
+    if (!lead_keep && (ld_out % 2 != 0 || ((uintptr_t)out % 16) != 0 || n % 2 != 0)) return 0;
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return 0;
+    const int kpad = (kdim + RT_KS - 1) / RT_KS * RT_KS;
+    const int ny = (n + RT_MAX_COLS - 1) / RT_MAX_COLS;
+    const int cols_per_cta = ((n + ny - 1) / ny + 7) / 8 * 8;      // balanced column blocks, multiples of 8
+    int np = cols_per_cta;
+    while (np % 16 != 2) ++np;
+    int dev = 0, smem_max = 0;
+    QIO_CUDA(cudaGetDevice(&dev));
+    QIO_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t fixed = sizeof(double) * (size_t)kpad * np + 2 * RT_MAX_STAGES * sizeof(unsigned long long) + 1024;
+    if (fixed + 3 * RT_STAGE_DOUBLES * sizeof(double) > (size_t)smem_max) return 0;
+    int stages = (int)(((size_t)smem_max - fixed) / (RT_STAGE_DOUBLES * sizeof(double)));
+    stages = stages > RT_MAX_STAGES ? RT_MAX_STAGES : stages;
+    const size_t smem = (size_t)stages * RT_STAGE_DOUBLES * sizeof(double) + fixed - 1024;
+
+    CUtensorMap tm;
+    const cuuint64_t gdim[3] = {16, (cuuint64_t)kdim, (cuuint64_t)(rows / 16)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)ld_in * sizeof(double), 16 * sizeof(double)};
+    const cuuint32_t box[3] = {16, RT_KS, RT_BM / 16};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(in), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return 0;
+    const long long mtiles = (rows + RT_BM - 1) / RT_BM;
+    const int gx = (int)std::min<long long>(mtiles, std::max(1, sm_count() / ny));
+    dim3 grid(gx, ny);
+    if (lead_keep) {
+        QIO_CUDA(cudaFuncSetAttribute(rotate_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rotate_tma_kernel<true><<<grid, RT_THREADS, smem, st>>>(tm, U, out, n, kdim, ldu, rows, ld_out, cols_per_cta, np, kpad, stages);
+    } else {
+        QIO_CUDA(cudaFuncSetAttribute(rotate_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rotate_tma_kernel<false><<<grid, RT_THREADS, smem, st>>>(tm, U, out, n, kdim, ldu, rows, ld_out, cols_per_cta, np, kpad, stages);
+    }
+    QIO_LAUNCH_CHECK();
+    return 1;
+}
+
+}  // namespace qio
