@@ -32,7 +32,7 @@ def rotated_case(n, seed=5, np_seed=1):
     U = O.random_start(n)
     return O.rotate_rdm1(U, gamma0), O.rotate_rdm2(U, Gamma0)
 
-
+@pytest.mark.parametrize('n', [1, 2, 6, 12, 31, 32, 33, 40, 52, 53, 54, 60, 105])   # 53+: several 52-wide tiles, ragged last tile
 # ---- a-1 ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('n', [1, 2, 6, 12, 31, 32, 33, 40])
 def test_prep_rdm12_bit_exact(n):
