@@ -336,6 +336,8 @@ def run_b200_arm(args):
     ms_per_step = ms_total / args.steps
     value = evals_per_step / (ms_per_step * 1e-3)
     launches_per_step = 2 + 1 + 4 + 1 + 1 + 1 + 1 + (1 + 1 + 1 + 1 + 1) + 3   # prep, rotations, all-pairs (+MI), sweep (+cost), flush
+    if dev.sweep_engine(n) == 3:
+        launches_per_step += 1      # per-pair table kernel of the pipelined sweep
 
     # ---- phase timings (explain the step) and the roofline of the dominant kernel ----------------------
     def timed(fn, reps=1):
@@ -389,15 +391,26 @@ def run_b200_arm(args):
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     achieved = algo_bytes / (sweep_ms * 1e-3) / 1e9
-    roofline = {'kernel': 'sweep_v2_kernel (persistent Jacobi cycle: line searches + Givens updates of rdm2)',
+    engine = dev.sweep_engine(n)
+    kname = ('sweep3_kernel (pipelined persistent Jacobi cycle: search CTA + reducers + column-owning workers)' if engine == 3
+             else 'sweep_kernel (persistent Jacobi cycle, one grid barrier per pair)')
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'sweep_traffic.json')
+    if os.path.exists(tpath):
+        ent = json.load(open(tpath)).get(f'engine{engine}', {}).get(str(n))
+        if ent:
+            traffic = ent['dram_bytes_per_accepted_rotation'] * n_accepted
+            traffic_src = f"{ent['source']}: {ent['dram_bytes_per_accepted_rotation'] / 1e6:.1f} MB per accepted rotation (ncu, {ent['accepted']} rotations) x {n_accepted}"
+    roofline = {'kernel': kname,
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'peak_source': peak_src, 'traffic': None, 'algorithmic_bytes_per_launch': algo_bytes,
+                'peak_source': peak_src, 'traffic': traffic, 'traffic_source': traffic_src, 'algorithmic_bytes_per_launch': algo_bytes,
                 'avg_launch_ms': sweep_ms, 'launches_timed': 1,
                 'kernel_min_bytes_per_launch': kernel_bytes,
                 'kernel_min_bytes_frac': kernel_bytes / (sweep_ms * 1e-3) / 1e9 / peak,
                 'note': 'algorithmic bytes = 16 (n^4-(n-2)^4) per accepted rotation (SURVEY 8d); the deferred-axis layout '
                         'moves only 64 n^3 B per rotation (+ 32 n^2 B of block rows per pair), see kernel_min_bytes_*; '
-                        'per-rotation working set %.0f MB vs 126 MB L2' % (32.0 * n ** 3 / 1e6)}
+                        'per-rotation working set %.0f MB vs 126 MB L2 (L2-resident: DRAM traffic below the algorithmic bytes, '
+                        'frac above 1 is possible)' % (32.0 * n ** 3 / 1e6)}
 
     # ---- e2e through the public API from pinned host memory ------------------------------------------------
     e2e = None
@@ -558,7 +571,8 @@ def run_b200_multi(args, rank, world, local_rank):
     peak = json.load(open(peaks_path))['hbm_gbs'] if os.path.exists(peaks_path) else 6650.0
     algo_bytes = 16.0 * (n ** 4 - (n - 2) ** 4) * n_acc / world
     achieved = algo_bytes / (sweep_ms * 1e-3) / 1e9
-    roofline = {'kernel': 'sweep_kernel (persistent Jacobi cycle), per GPU', 'bound': 'hbm', 'achieved': achieved,
+    engine = dev.sweep_engine(n, na)
+    roofline = {'kernel': ('sweep3_kernel (pipelined persistent Jacobi cycle)' if engine == 3 else 'sweep_kernel (persistent Jacobi cycle, grid barrier per pair)') + ', per GPU', 'bound': 'hbm', 'achieved': achieved,
                 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                 'algorithmic_bytes_per_launch': algo_bytes, 'avg_launch_ms': sweep_ms, 'launches_timed': 1,
                 'kernel_min_bytes_per_launch': (64.0 * n ** 3 * n_acc + 32.0 * n * n * len(pairs_np)) / world,

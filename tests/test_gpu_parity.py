@@ -4,6 +4,7 @@ against golden vectors produced by the real reference.  Run on the B200 box: pyt
 Tolerances: bit-exact for prep_rdm12, pair order, accepted angles (they are table entries); 1e-10
 absolute for entropies / costs (north_star); 1e-10 relative for gradient / Hessian entries, which the
 reference divides by spectrum entries that can be tiny."""
+import os
 import warnings
 
 import numpy as np
@@ -32,9 +33,9 @@ def rotated_case(n, seed=5, np_seed=1):
     U = O.random_start(n)
     return O.rotate_rdm1(U, gamma0), O.rotate_rdm2(U, Gamma0)
 
-@pytest.mark.parametrize('n', [1, 2, 6, 12, 31, 32, 33, 40, 52, 53, 54, 60, 105])   # 53+: several 52-wide tiles, ragged last tile
+
 # ---- a-1 ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('n', [1, 2, 6, 12, 31, 32, 33, 40])
+@pytest.mark.parametrize('n', [1, 2, 6, 12, 31, 32, 33, 40, 52, 53, 54, 60])   # 53+: several 52-wide tiles, ragged last tile
 def test_prep_rdm12_bit_exact(n):
     rng = np.random.default_rng(n)
     dm1 = rng.standard_normal((n, n))
@@ -307,13 +308,24 @@ def test_deferred_engine_matches_materialized_engine(n):
     order = np.random.default_rng(n).permutation(n)
     pairs = JA.sweep_pairs(order, inact)
     out = {}
-    for engine in ('materialized', 'deferred'):
-        gd, Gd, Ud = dev.to_device(g).clone(), dev.to_device(G).clone(), dev.to_device(np.eye(n)).clone()
-        st = JA.SweepState(gd, Gd, Ud, n, inact, engine=engine)
-        rec1, acc1, cost1, _ = st.cycle(pairs)
-        rec2, acc2, cost2, _ = st.cycle(pairs[::-1].copy())          # second cycle on the deferred state
-        gg, GG = st.finish()
+    for engine in ('materialized', 'deferred', 'deferred-barrier'):
+        if engine == 'deferred-barrier':
+            os.environ['QIO_B200_SWEEP_ENGINE'] = '2'
+        try:
+            gd, Gd, Ud = dev.to_device(g).clone(), dev.to_device(G).clone(), dev.to_device(np.eye(n)).clone()
+            st = JA.SweepState(gd, Gd, Ud, n, inact, engine=engine.split('-')[0])
+            rec1, acc1, cost1, _ = st.cycle(pairs)
+            rec2, acc2, cost2, _ = st.cycle(pairs[::-1].copy())          # second cycle on the deferred state
+            gg, GG = st.finish()
+        finally:
+            os.environ.pop('QIO_B200_SWEEP_ENGINE', None)
         out[engine] = (rec1, rec2, cost1, cost2, dev.to_host(gg), dev.to_host(GG), dev.to_host(Ud))
+    # the pipelined and the barrier kernel sum the same partial products in different orders: same decisions
+    c = out['deferred-barrier']
+    for k in (0, 1):
+        assert np.array_equal(c[k]['accepted'], out['deferred'][k]['accepted'])
+        assert np.array_equal(c[k]['theta'], out['deferred'][k]['theta'], equal_nan=True)
+    assert np.allclose(c[5], out['deferred'][5], atol=1e-12, rtol=0)
     a, b = out['materialized'], out['deferred']
     for k in (0, 1):
         assert np.array_equal(a[k]['accepted'], b[k]['accepted'])
@@ -327,8 +339,16 @@ def test_deferred_engine_matches_materialized_engine(n):
     assert abs(get_cost_fqi(b[4], b[5], inact) - b[3]) < 1e-12
 
 
-@pytest.mark.parametrize('engine', ['deferred', 'materialized'])
+@pytest.mark.parametrize('engine', ['deferred', 'deferred-barrier', 'materialized'])
 def test_jacobi_driver_golden_rotations_bit_exact(golden, engine, monkeypatch):
+    """'deferred' = the pipelined kernel (sweep3.cu), 'deferred-barrier' = the same state with one grid barrier per pair
+    (sweep2.cu, forced through the environment switch), 'materialized' = one launch per pair on the natural layout."""
+    if engine == 'deferred-barrier':
+        monkeypatch.setenv('QIO_B200_SWEEP_ENGINE', '2')
+        engine = 'deferred'
+        assert dev.sweep_engine(int(golden['n'])) == 2
+    else:
+        monkeypatch.delenv('QIO_B200_SWEEP_ENGINE', raising=False)
     monkeypatch.setattr(JA, 'ENGINE', engine)
     gamma0, Gamma0 = prepared_inputs(golden)
     n = int(golden['n'])
