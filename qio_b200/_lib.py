@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libqio_b200.so')
+LIB_PATH = os.environ.get('QIO_B200_LIB') or os.path.join(_HERE, 'csrc', 'libqio_b200.so')   # override: A/B builds
 
 BLOCK_DOUBLES = 24
 FLAG_WARN_NEGATIVE = 1

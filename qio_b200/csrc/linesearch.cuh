@@ -6,12 +6,14 @@
 //           strictly below cost(0); otherwise t_opt falls back to 0.01 == coarse point 0;
 //   fine:   accept k iff cost > cost_k + 1e-8, then cost = cost_k.  The chain is sequential in
 //           principle, but it decomposes into "find the first k beyond the last accepted one with
-//           cost_k + 1e-8 < cost" (a ballot over 256 threads) followed by a run of consecutive accepts
+//           cost_k + 1e-8 < cost" (ballots of one warp that holds all entries) followed by a run of consecutive accepts
 //           (a_k := cost_{k-1} > cost_k + 1e-8, precomputed as a bit mask).  A smooth cost curve needs
 //           two rounds; any other sequence just takes more rounds with the same result.
 // The NT participating threads (the first NT of the CTA) synchronise on a NAMED barrier, so a CTA may
 // have more threads that do something else (or wait elsewhere) meanwhile.
 #pragma once
+#include <type_traits>
+
 #include "pair_math.cuh"
 
 namespace qio {
@@ -43,14 +45,14 @@ template <int NT>
 struct LineSearchSmemT {
     double fine_val[LS_MAX_FINE];     // cost at each fine angle
     double fine_thr[LS_MAX_FINE];     // cost + 1e-8 (rounded add, as the reference's `new_cost + 1e-8`)
-    unsigned amask[LS_MAX_FINE / 32]; // bit k: cost_{k-1} > cost_k + 1e-8
-    unsigned accmask[LS_MAX_FINE / 32];   // bit k: entry k was accepted by the scan
-    int wfirst[LS_MAX_FINE / 32];
+    double2 fine_cs[LS_MAX_FINE];     // cos, sin of each fine angle
+    int scan_last;                    // results of warp 0's accept scan
+    double scan_cur;
+    unsigned accw[LS_MAX_FINE / 32];  // bit k: entry k was accepted by the scan
     double wmargin[LS_MAX_FINE / 32];
     MinIdx warp_best[NT / 32];
     MinIdx best;
     double cost0;
-    double cs_acc[2];                 // cos, sin of the accepted angle
     int flags;
     long long prof[8];                // cycles thread 0 spent per stage (coarse, reduce, fine, scan, margin, tail)
     long long prof_last;
@@ -69,25 +71,29 @@ __device__ __forceinline__ void ls_sync() {
     asm volatile("bar.sync %0, %1;" ::"n"(LS_BARRIER), "n"(NT) : "memory");
 }
 
-__device__ __forceinline__ double warp_min_double(double v) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
-    return v;
-}
+__device__ __forceinline__ double warp_min_double(double v) { return dunkey(warp_min_u64(dkey(v))); }
 
 // Threads 0..NT-1 of the CTA (whole warps, NT >= 256) must call this with the same arguments; the others must not.
 // The result is returned in every participating thread.  `b` is either a PairBlock / PairBlockRef (reference operation
 // order) or a PairCoef (fast polynomial form): pair_cost() is overloaded.
-template <int NT, typename Block>
+struct NoDecisionHook {
+    __device__ __forceinline__ void operator()(bool, double, double) const {}
+};
+
+// `decided(accepted, cos, sin)` is called by thread 0 as soon as the angle is known (before the margins are taken): the
+// pipelined sweep publishes the angle there.
+template <int NT, typename Block, typename Hook = NoDecisionHook>
 __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool j_in, const ThetaTablesDev &tab,
-                                                 LineSearchSmemT<NT> &sm, qio_b200_ls_result &res) {
+                                                 LineSearchSmemT<NT> &sm, qio_b200_ls_result &res, Hook decided = Hook()) {
     static_assert(NT >= LS_MAX_FINE && NT % 32 == 0, "line search needs at least 256 threads");
     constexpr int NW = LS_MAX_FINE / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int flags = 0;
     if (tid == 0) {
         sm.prof_last = clock64();
-        sm.flags = 0;
+        // PairCoef (fast) evaluations OR their flags straight into sm.flags: the CALLER zeroes it (thread 0, next to
+        // make_coef, before the barrier that precedes this call); the other block types collect flags per thread
+        if (!std::is_same<Block, PairCoef>::value) sm.flags = 0;
     }
 
     // ---- coarse grid; candidate index n_coarse is theta = 0 (cos = 1, sin = 0 exactly as np.cos(0)) ----
@@ -96,11 +102,14 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
     mine.idx = 0x7fffffff;
     mine.v2 = INFINITY;
     for (int t = tid; t <= tab.n_coarse; t += NT) {
-        if (t == tab.n_coarse) {
-            sm.cost0 = pair_cost(b, 1.0, 0.0, i_in, j_in, flags);
+        // one evaluation site for both the grid points and theta = 0 (the pair cost is inlined: a call would spill the
+        // caller's live registers to local memory around it, and those reloads miss L1 in the persistent kernels)
+        const bool zero = (t == tab.n_coarse);
+        const double2 cs = zero ? make_double2(1.0, 0.0) : reinterpret_cast<const double2 *>(tab.coarse_cs)[t];
+        double v = pair_cost(b, cs.x, cs.y, i_in, j_in, flags, &sm.flags);
+        if (zero) {
+            sm.cost0 = v;
         } else {
-            const double2 cs = reinterpret_cast<const double2 *>(tab.coarse_cs)[t];
-            double v = pair_cost(b, cs.x, cs.y, i_in, j_in, flags);
             if (!(v == v)) v = INFINITY;            // a NaN never wins a '>' comparison
             MinIdx cand;
             cand.v = v;
@@ -131,92 +140,96 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
         double v = INFINITY;
         if (tid < L) {
             my_cs = fcs[tid];
-            v = pair_cost(b, my_cs.x, my_cs.y, i_in, j_in, flags);
+            v = pair_cost(b, my_cs.x, my_cs.y, i_in, j_in, flags, &sm.flags);
         }
         my_thr = __dadd_rn(v, 1e-8);                // +inf (or NaN) beyond L: never accepted
         sm.fine_val[tid] = v;
         sm.fine_thr[tid] = my_thr;
+        sm.fine_cs[tid] = my_cs;
     }
     if (flags) atomicOr(&sm.flags, flags);
     ls_sync<NT>();
     LS_PROF(2)
 
-    // ---- the accept scan (warps 0..7 hold one fine entry per thread) -------------------------------
-    if (tid < LS_MAX_FINE) {
-        const bool a = tid > 0 && tid < L && sm.fine_val[tid - 1] > my_thr;
-        const unsigned m = __ballot_sync(0xffffffffu, a);
+    // ---- the accept scan, by warp 0 alone (lane l holds the entries l, l + 32, ...): no CTA-wide barrier inside the
+    // rounds, one warp-wide integer minimum per round ----------------------------------------------------------------
+    if (warp == 0) {
+        double thr[NW];
+        unsigned am[NW], accw[NW];
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            const int k = lane + 32 * j;
+            thr[j] = sm.fine_thr[k];
+            const bool a = k > 0 && k < L && sm.fine_val[k > 0 ? k - 1 : 0] > thr[j];     // cost_{k-1} > cost_k + 1e-8
+            am[j] = __ballot_sync(0xffffffffu, a);
+            accw[j] = 0u;
+        }
+        int last = -1;          // last accepted index (uniform)
+        double cur = start;     // running cost (uniform)
+        for (;;) {
+            // first k beyond `last` with cost_k + 1e-8 < cost (k < L implied: thr = +inf beyond)
+            int mine = 0x7fffffff;
+#pragma unroll
+            for (int j = NW - 1; j >= 0; --j)
+                if (lane + 32 * j > last && thr[j] < cur) mine = lane + 32 * j;
+            const int first = (int)__reduce_min_sync(0xffffffffu, (unsigned)mine);
+            if (first == 0x7fffffff) break;
+            // extend over the run of consecutive accepts that follows: first zero bit of the mask above `first`
+            // (bits at and beyond L are zero by construction, so the run always ends before L)
+            int e = LS_MAX_FINE - 1;
+            {
+                int w = (first + 1) >> 5;
+                unsigned zeros = w < NW ? ~am[0] : 0u;
+#pragma unroll
+                for (int q = 1; q < NW; ++q) zeros = (w == q) ? ~am[q] : zeros;
+                if (w < NW) zeros &= ~0u << ((first + 1) & 31);
+                while (w < NW && !zeros) {
+                    ++w;
+                    zeros = 0u;
+#pragma unroll
+                    for (int q = 1; q < NW; ++q) zeros = (w == q) ? ~am[q] : zeros;
+                }
+                if (w < NW) e = w * 32 + __ffs(zeros) - 2;                       // last set bit before the first zero
+            }
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {                                   // record the accepted run [first, e]
+                const int lo = max(first, w * 32), hi = min(e, w * 32 + 31);
+                if (lo <= hi) accw[w] |= (hi - lo == 31 ? ~0u : ((1u << (hi - lo + 1)) - 1u) << (lo - w * 32));
+            }
+            last = e;
+            cur = sm.fine_val[e];
+        }
         if (lane == 0) {
-            sm.amask[warp] = m;
-            sm.accmask[warp] = 0;
+            sm.scan_last = last;
+            sm.scan_cur = cur;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) sm.accw[w] = accw[w];
         }
     }
     ls_sync<NT>();
-    int last = -1;          // last accepted index (uniform over the participants)
-    double cur = start;     // running cost (uniform)
-    unsigned am[NW];
-#pragma unroll
-    for (int w = 0; w < NW; ++w) am[w] = sm.amask[w];
-    for (;;) {
-        if (tid < LS_MAX_FINE) {
-            const bool pred = tid > last && my_thr < cur;       // tid < L implied (thr = +inf beyond)
-            const unsigned m = __ballot_sync(0xffffffffu, pred);
-            if (lane == 0) sm.wfirst[warp] = m ? (warp * 32 + __ffs(m) - 1) : 0x7fffffff;
-        }
-        ls_sync<NT>();
-        int first = 0x7fffffff;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) first = min(first, sm.wfirst[w]);
-        if (first == 0x7fffffff) break;
-        // extend over the run of consecutive accepts that follows: first zero bit of the mask above `first`
-        // (bits at and beyond L are zero by construction, so the run always ends before L)
-        int e = LS_MAX_FINE - 1;
-        bool found = false;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const int base = w * 32;
-            unsigned zeros = ~am[w];                                     // candidate run ends (bit k clear)
-            if (first + 1 >= base + 32) zeros = 0;                       // word entirely at or below `first`
-            else if (first + 1 > base) zeros &= ~0u << (first + 1 - base);
-            if (!found && zeros) {
-                e = base + __ffs(zeros) - 2;                             // last set bit before the first zero
-                found = true;
-            }
-        }
-        if (tid < LS_MAX_FINE && lane == 0) {                            // record the accepted run [first, e]
-            const int lo = max(first, warp * 32), hi = min(e, warp * 32 + 31);
-            if (lo <= hi) sm.accmask[warp] |= (hi - lo == 31 ? ~0u : ((1u << (hi - lo + 1)) - 1u) << (lo - warp * 32));
-        }
-        last = e;
-        cur = sm.fine_val[e];
-        ls_sync<NT>();        // wfirst is rewritten in the next round
-    }
-    if (tid == last) {
-        sm.cs_acc[0] = my_cs.x;
-        sm.cs_acc[1] = my_cs.y;
-    }
+    const int last = sm.scan_last;
+    const double cur = sm.scan_cur;
+    if (tid == 0) decided(last >= 0, last >= 0 ? sm.fine_cs[last].x : 1.0, last >= 0 ? sm.fine_cs[last].y : 0.0);
     LS_PROF(3)
 
-    // ---- smallest |cost - (new_cost + 1e-8)| over every comparison of the reference's scan ---------------
-    // entry k was compared against the cost of the last accepted entry before k (or the starting cost)
-    ls_sync<NT>();
+    // ---- smallest |cost - (new_cost + 1e-8)| over every comparison of the reference's scan: entry k was compared
+    // against the cost of the last accepted entry before k (or the starting cost); one entry per thread -----------
     if (tid < LS_MAX_FINE) {
-        unsigned accw[NW];
-#pragma unroll
-        for (int w = 0; w < NW; ++w) accw[w] = sm.accmask[w];
-        int prev = -1;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            unsigned m = accw[w];
-            if (w > warp) m = 0;
-            else if (w == warp) m &= (lane == 0) ? 0u : (~0u >> (32 - lane));     // bits below this thread's entry
-            if (m) prev = w * 32 + 31 - __clz(m);
-        }
         double mg = INFINITY;
-        if (tid < L) mg = fabs((prev >= 0 ? sm.fine_val[prev] : start) - my_thr);
+        if (tid < L) {
+            int prev = -1;
+            unsigned m = sm.accw[warp] & ((lane == 0) ? 0u : (~0u >> (32 - lane)));      // bits below this entry
+            int w = warp;
+            while (!m && w > 0) m = sm.accw[--w];
+            if (m) prev = w * 32 + 31 - __clz(m);
+            mg = fabs((prev >= 0 ? sm.fine_val[prev] : start) - my_thr);
+        }
         mg = warp_min_double(mg);
         if (lane == 0) sm.wmargin[warp] = mg;
     }
+    LS_PROF(6)
     ls_sync<NT>();
+    LS_PROF(7)
     double margin = INFINITY;
 #pragma unroll
     for (int w = 0; w < NW; ++w) margin = fmin(margin, sm.wmargin[w]);
@@ -232,8 +245,8 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
     res.fine_margin = margin;
     if (fidx >= 0) {
         res.theta = tab.fine_theta[(size_t)row * tab.fine_stride + fidx];     // for the record only
-        res.cos_theta = sm.cs_acc[0];
-        res.sin_theta = sm.cs_acc[1];
+        res.cos_theta = sm.fine_cs[fidx].x;
+        res.sin_theta = sm.fine_cs[fidx].y;
     } else {
         res.theta = __longlong_as_double(0x7ff8000000000000LL);
         res.cos_theta = 1.0;

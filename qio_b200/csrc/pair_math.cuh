@@ -89,7 +89,7 @@ __device__ __forceinline__ double rotated_orbital_entropy(const Block &b, double
 
 // jacobi_cost(theta, i, j, ...) given cos/sin: S(i') if i inactive, plus S(j') if j inactive.
 template <typename Block>
-__device__ __forceinline__ double pair_cost(const Block &b, double c, double s, bool i_in, bool j_in, int &flags) {
+__device__ __forceinline__ double pair_cost(const Block &b, double c, double s, bool i_in, bool j_in, int &flags, int * /*sink*/ = nullptr) {
     double total = 0.0;
     if (i_in) total = __dadd_rn(total, rotated_orbital_entropy(b, c, s, flags));
     if (j_in) total = __dadd_rn(total, rotated_orbital_entropy(b, -s, c, flags));
@@ -240,24 +240,40 @@ __device__ __forceinline__ double masked_entropy3_sym(double s0, double s1, doub
     return -(((term[0] + term[1]) + term[1]) + term[2]);
 }
 
-static __device__ __noinline__ double pair_cost(const PairCoef &pc, double c, double s, bool i_in, bool j_in, int &flags) {
+// Two variants (spin-symmetric: 2 x 3 logarithms; general: 2 x 4), both inlined into the line search (two sites).
+// Flags (warn / raise conditions, rare) go straight to `sink` (a shared- or global-memory word): a by-reference int would
+// live in local memory and cost every call a load and a store there.
+__device__ __forceinline__ double pair_cost_sym(double A0, double A1, double A2, double A3, double A4, double g0, double g1,
+                                                    double g2, double c, double s, bool i_in, bool j_in, int *sink) {
+    const double c2 = c * c, s2 = s * s, cs = c * s, c2s2 = c2 * s2;
+    const double nn_i = c2 * (A0 * c2 + A1 * cs) + A2 * c2s2 + s2 * (A3 * cs + A4 * s2);
+    const double nn_j = s2 * (A0 * s2 - A1 * cs) + A2 * c2s2 + c2 * (A4 * c2 - A3 * cs);
+    const double nu_i = g0 * c2 + g1 * cs + g2 * s2, nu_j = g0 * s2 - g1 * cs + g2 * c2;
+    int fi = 0, fj = 0;       // nd == nu bit for bit
+    const double Si = masked_entropy3_sym(1.0 - nu_i - nu_i + nn_i, nu_i - nn_i, nn_i, fi);
+    const double Sj = masked_entropy3_sym(1.0 - nu_j - nu_j + nn_j, nu_j - nn_j, nn_j, fj);
+    const int f = (i_in ? fi : 0) | (j_in ? fj : 0);
+    if (f) atomicOr(sink, f);
+    return (i_in ? Si : 0.0) + (j_in ? Sj : 0.0);
+}
+
+__device__ __forceinline__ double pair_cost_gen(const PairCoef &pc, double c, double s, bool i_in, bool j_in, int *sink) {
     const double c2 = c * c, s2 = s * s, cs = c * s, c2s2 = c2 * s2;
     const double nn_i = c2 * (pc.A[0] * c2 + pc.A[1] * cs) + pc.A[2] * c2s2 + s2 * (pc.A[3] * cs + pc.A[4] * s2);
     const double nn_j = s2 * (pc.A[0] * s2 - pc.A[1] * cs) + pc.A[2] * c2s2 + c2 * (pc.A[4] * c2 - pc.A[3] * cs);
     const double nu_i = pc.gu[0] * c2 + pc.gu[1] * cs + pc.gu[2] * s2, nu_j = pc.gu[0] * s2 - pc.gu[1] * cs + pc.gu[2] * c2;
-    if (pc.sym) {       // nd == nu bit for bit
-        int fi = 0, fj = 0;
-        const double Si = masked_entropy3_sym(1.0 - nu_i - nu_i + nn_i, nu_i - nn_i, nn_i, fi);
-        const double Sj = masked_entropy3_sym(1.0 - nu_j - nu_j + nn_j, nu_j - nn_j, nn_j, fj);
-        flags |= (i_in ? fi : 0) | (j_in ? fj : 0);
-        return (i_in ? Si : 0.0) + (j_in ? Sj : 0.0);
-    }
     const double nd_i = pc.gd[0] * c2 + pc.gd[1] * cs + pc.gd[2] * s2, nd_j = pc.gd[0] * s2 - pc.gd[1] * cs + pc.gd[2] * c2;
     int fi = 0, fj = 0;
     const double Si = masked_entropy4_fast(1.0 - nu_i - nd_i + nn_i, nu_i - nn_i, nd_i - nn_i, nn_i, fi);
     const double Sj = masked_entropy4_fast(1.0 - nu_j - nd_j + nn_j, nu_j - nn_j, nd_j - nn_j, nn_j, fj);
-    flags |= (i_in ? fi : 0) | (j_in ? fj : 0);
+    const int f = (i_in ? fi : 0) | (j_in ? fj : 0);
+    if (f) atomicOr(sink, f);
     return (i_in ? Si : 0.0) + (j_in ? Sj : 0.0);
+}
+
+__device__ __forceinline__ double pair_cost(const PairCoef &pc, double c, double s, bool i_in, bool j_in, int & /*flags*/, int *sink) {
+    if (pc.sym) return pair_cost_sym(pc.A[0], pc.A[1], pc.A[2], pc.A[3], pc.A[4], pc.gu[0], pc.gu[1], pc.gu[2], c, s, i_in, j_in, sink);
+    return pair_cost_gen(pc, c, s, i_in, j_in, sink);
 }
 
 // Analytic d/dtheta and d2/dtheta2 of the pair cost at theta = 0 (qio/grad/gradient.py:13-120),
@@ -324,16 +340,30 @@ __device__ __forceinline__ MinIdx merge(const MinIdx &a, const MinIdx &b) {
     return r;
 }
 
+// Order-preserving map double -> unsigned 64-bit (all finite values and +-inf; NaN is mapped by the callers beforehand).
+__device__ __forceinline__ unsigned long long dkey(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+// Warp-wide minimum of a 64-bit key with two hardware reductions (REDUX) instead of five shuffle rounds.
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k) {
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+
+// Same result as a merge() tree over the lanes: first index of the minimum, second best value among the OTHER indices.
 __device__ __forceinline__ MinIdx warp_min(MinIdx x) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        MinIdx y;
-        y.v = __shfl_xor_sync(0xffffffffu, x.v, off);
-        y.idx = __shfl_xor_sync(0xffffffffu, x.idx, off);
-        y.v2 = __shfl_xor_sync(0xffffffffu, x.v2, off);
-        x = merge(x, y);
-    }
-    return x;
+    const unsigned long long key = dkey(x.v), kmin = warp_min_u64(key);
+    MinIdx r;
+    r.v = dunkey(kmin);
+    r.idx = (int)__reduce_min_sync(0xffffffffu, key == kmin ? (unsigned)x.idx : 0x7fffffffu);
+    r.v2 = dunkey(warp_min_u64(dkey(x.idx == r.idx ? x.v2 : x.v)));
+    return r;
 }
 
 }  // namespace qio

@@ -171,7 +171,10 @@ __global__ void __launch_bounds__(LS_THREADS)
             load_block(rec, b);
             cta_linesearch(b, inactive[i] != 0, inactive[j] != 0, tab, sm, res);
         } else {
-            if (threadIdx.x == 0) make_coef(rec, pc);
+            if (threadIdx.x == 0) {
+                make_coef(rec, pc);
+                sm.flags = 0;
+            }
             __syncthreads();
             cta_linesearch_t<LS_THREADS, PairCoef>(pc, inactive[i] != 0, inactive[j] != 0, tab, sm, res);
         }

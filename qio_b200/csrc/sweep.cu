@@ -38,7 +38,10 @@ __global__ void __launch_bounds__(LS_THREADS)
     }
     __shared__ PairCoef pc;
     __syncthreads();
-    if (threadIdx.x == 0) make_coef(rec, pc);
+    if (threadIdx.x == 0) {
+        make_coef(rec, pc);
+        sm.flags = 0;
+    }
     __syncthreads();
     qio_b200_ls_result res;
     cta_linesearch_t<LS_THREADS, PairCoef>(pc, inactive[i] != 0, inactive[j] != 0, tab, sm, res);

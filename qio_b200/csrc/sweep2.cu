@@ -615,6 +615,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepParams p) {
             c0 = clock64();
             target_matrix(tg, Tmat);
         }
+        if (tid == 0) ls.flags = 0;         // the fast pair cost ORs its flags straight into it (see linesearch.cuh)
         const bool i_in = p.inactive[i] != 0, j_in = p.inactive[j] != 0;       // L2 latency overlaps the contraction
         ls_sync<SEARCH_THREADS>();
         block_from_superblock(sb, Tmat, sbtmp, blk, pc);

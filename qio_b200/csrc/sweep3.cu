@@ -993,7 +993,10 @@ __device__ __forceinline__ void search_main(const Params &p, SearchSmem &sm) {
                 sm.blk[tid] = acc;
             }
             ls_sync<SEARCH_THREADS>();
-            if (tid == 0) make_coef(sm.blk, sm.pc);
+            if (tid == 0) {
+                make_coef(sm.blk, sm.pc);
+                sm.ls.flags = 0;
+            }
             ls_sync<SEARCH_THREADS>();
         }
         named_arrive_id<THREADS>(4 + b);                    // empty[b]: the prefetch warps may overwrite sm.sb[b]
@@ -1003,15 +1006,18 @@ __device__ __forceinline__ void search_main(const Params &p, SearchSmem &sm) {
             tq = t;
         }
         qio_b200_ls_result res;
-        cta_linesearch_t<SEARCH_THREADS, PairCoef>(sm.pc, i_in, j_in, tab, sm.ls, res);
+        // the angle record is published by thread 0 the moment the scan has decided (before the margins are taken)
+        auto publish = [&](bool accepted, double cth, double sth) {
+            unsigned long long *w = p.ring + (size_t)(k & (RING - 1)) * 4;
+            const unsigned long long tag = 2ull * (unsigned long long)(k + 1) + (accepted ? 1ull : 0ull);
+            ll_store(w, (unsigned long long)__double_as_longlong(cth), tag);
+            ll_store(w + 2, (unsigned long long)__double_as_longlong(sth), tag);
+        };
+        cta_linesearch_t<SEARCH_THREADS, PairCoef>(sm.pc, i_in, j_in, tab, sm.ls, res, publish);
         if (tid == 0) {
             const unsigned long long t = gtimer();
             t_search += t - tq;
             tq = t;
-            unsigned long long *w = p.ring + (size_t)(k & (RING - 1)) * 4;
-            const unsigned long long tag = 2ull * (unsigned long long)(k + 1) + (res.accepted ? 1ull : 0ull);
-            ll_store(w, (unsigned long long)__double_as_longlong(res.cos_theta), tag);
-            ll_store(w + 2, (unsigned long long)__double_as_longlong(res.sin_theta), tag);
             p.results[k] = res;
             const unsigned long long t2 = gtimer();
             t_pub += t2 - tq;
@@ -1036,6 +1042,8 @@ __device__ __forceinline__ void search_main(const Params &p, SearchSmem &sm) {
         p.summary[8] = 0.0;
         p.summary[9] = (double)t_setup;       // T, contraction, coefficients
         for (int q = 0; q < 6; ++q) p.summary[10 + q] = (double)sm.ls.prof[q];
+        p.summary[25] = (double)sm.ls.prof[6];
+        p.summary[26] = (double)sm.ls.prof[7];
         p.summary[24] = 3.0;                  // engine id
     }
 }
