@@ -54,6 +54,9 @@ constexpr int TILE_PITCH = 98;   // row pitch of the tile: 196 words = 4 mod 32,
 constexpr int DT_STRIDE = 16;     // ints per entry of the per-pair table
 constexpr int WORK_THREADS = THREADS - 32;   // a worker's warps 0..14 compute, warp 15 plans the next step (polls the angle)
 constexpr int TILE_THREADS = WORK_THREADS;   // all working warps do the tile phase, then the flat phase
+constexpr int MAXN3 = 1024;      // largest n of the pipelined kernel (rank / activation tables in shared memory)
+constexpr int CU_COLS = 32;       // columns per catch-up chunk (one per lane)
+constexpr int CU_PRE = 8;         // row prefetch registers of the catch-up (rows up to 256 entries)
 constexpr int NRED = 4;          // reducer CTAs (each sums a quarter of the entries)
 constexpr unsigned long long TIMEOUT_NS = 4000000000ull;
 constexpr int AUX_CTA = NRED + 1;
@@ -81,6 +84,8 @@ struct Params {
     int granule;                // doubles per ownership quantum (4, 2 or 1)
     int wc_cols;                // row pitch of a worker's private W columns
     double *wg;                 // [nworkers][n][wc_cols] every worker's own columns of W (global, L2-resident, private)
+    double *rg;                 // [nworkers][n][n] every worker's copy of the rotation accumulated in this launch, in
+                                // activation-rank coordinates (see the dormant-orbital note at catch_up)
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -225,6 +230,8 @@ struct WorkerStep {             // built by thread 0 of a worker for each step, 
     int tpos[MAXM];             // position of D_q in E
     int slot;                   // super-block index (k) this step produces, -1 if none
     int alive;
+    int nnew, na_before;        // orbitals that wake up in this step (first appearance in a super block), active count before
+    int newc[MAXM];
 };
 
 struct WorkerSmem {
@@ -232,7 +239,13 @@ struct WorkerSmem {
     int npieces, ncols, ncd;    // ncd = owned d-columns (concatenated over the pieces); ncols = ncd + npieces
     WorkerStep st[2];           // double-buffered: the planner warp writes step w + 1 while step w runs
     unsigned long long t_tile, t_wait, t_pass, t_flat;
-    unsigned skipmask[2][128];  // bit x: rows with index x are handled by the tile phase of that step (n <= 4096)
+    unsigned skipmask[2][MAXN3 / 32];   // bit x: the flat phase of that step leaves rows with index x alone (tile phase or dormant)
+    unsigned dorm[MAXN3 / 32];  // planner: bit x = orbital x has not appeared in any super block of this launch yet
+    short rank[MAXN3];          // activation rank of an orbital (-1: dormant); append-only
+    short alist[MAXN3];         // orbital of an activation rank
+    int na_act, any_rot;
+    short flatlist[2][MAXN3];   // per step: the row indices the flat phase visits (active, not in the tile), ascending
+    int nflat[2];
     double dots[MAX_PIECES * MAXM * MAXM * MAXM];       // [piece][q][r][s]
     alignas(16) double tile[MAXE * MAXE * TILE_PITCH];
 };
@@ -245,13 +258,13 @@ __device__ __forceinline__ int piece_of(const WorkerSmem &sm, int cc) {
     return pc;
 }
 
-// Flat phase of a worker: items [first, last) of the (axis, x, vector column) space of its owned columns, strided over
-// `nt` threads (this one is number t): rows (i, x), (j, x) (axis 0) or (x, i), (x, j) (axis 1) rotated by (c, s).  Rows whose
-// bit is set in `skipmask` belong to the tile phase.  A separate function on purpose: its loop wants a clean register file
+// Flat phase of a worker: the (axis, x, vector column) items of its owned columns for the `nflat` row indices x of
+// `flatlist` (active orbitals outside the tile), strided over `nt` threads (this one is number t): rows (i, x), (j, x)
+// (axis 0) or (x, i), (x, j) (axis 1) rotated by (c, s).  A separate function on purpose: its loop wants a clean register file
 // (four butterflies = eight independent 16-byte loads in flight per thread).
 template <int V>
-static __device__ __noinline__ void flat_update(double *__restrict__ S, const WorkerSmem *smp, const unsigned *skipmask, int n, int i,
-                                                int j, double c, double s, long long first, long long last, int t, int nt) {
+static __device__ __noinline__ void flat_update(double *__restrict__ S, const WorkerSmem *smp, const short *flatlist, int nflat, int n,
+                                                int i, int j, double c, double s, int t, int nt) {
     using VT = typename std::conditional<V == 2, double2, double>::type;
     constexpr int UNR = 4;
     const WorkerSmem &sm = *smp;
@@ -260,22 +273,26 @@ static __device__ __noinline__ void flat_update(double *__restrict__ S, const Wo
     const long long b0 = sm.piece[0].base, b1 = sm.piece[1].base, b2 = sm.piece[2].base, b3 = sm.piece[3].base;
     const int c1 = sm.npieces > 1 ? sm.piece[1].col0 : 0x7fffffff, c2 = sm.npieces > 2 ? sm.piece[2].col0 : 0x7fffffff,
               c3 = sm.npieces > 3 ? sm.piece[3].col0 : 0x7fffffff;
-    // mixed-radix counter (rho2, v) advanced by nt items
+    // mixed-radix counter (rho2, v) advanced by nt items; rho2 < 2 nflat: axis = rho2 >= nflat, x = flatlist[rho2 - axis nflat]
     const int dq = nt / lv, dr = nt - dq * lv;
-    long long item = first + t;
+    const long long last = 2LL * nflat * lv;
+    long long item = t;
     int rho2 = (int)(item / lv), v = (int)(item - (long long)rho2 * lv);
+    const long long safe = b0;          // a valid element offset for the loads of the items beyond the end
     while (item < last) {
         long long off[UNR];
         VT x[UNR], y[UNR];
+        unsigned okmask = 0u;
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const bool in = item < last;
-            const int axis = rho2 >= n ? 1 : 0, xx = in ? rho2 - axis * n : 0;
-            const bool skip = !in || ((skipmask[xx >> 5] >> (xx & 31)) & 1u);
+            const int axis = rho2 >= nflat ? 1 : 0, xx = in ? flatlist[rho2 - axis * nflat] : 0;
             const int cc = v * V;
             const long long pb = cc >= c3 ? b3 : (cc >= c2 ? b2 : (cc >= c1 ? b1 : b0));
-            // bit 62 of the offset carries the axis
-            off[u] = skip ? -1 : ((pb + cc + (axis ? xx * n2 : xx * n1)) | ((long long)axis << 62));
+            // bit 62 of the offset carries the axis; items beyond the end load (and do not store) a harmless valid element,
+            // so that every load is unconditional and the loaded values stay in registers
+            off[u] = (in ? (pb + cc + (axis ? xx * n2 : xx * n1)) : safe) | ((long long)axis << 62);
+            okmask |= in ? (1u << u) : 0u;
             item += nt;
             v += dr;
             rho2 += dq;
@@ -285,17 +302,16 @@ static __device__ __noinline__ void flat_update(double *__restrict__ S, const Wo
             }
         }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u)
-            if (off[u] >= 0) {
-                const bool ax = (off[u] >> 62) & 1;
-                const long long o = off[u] & ~(1LL << 62);
-                const long long si = ax ? (long long)i * n1 : (long long)i * n2, sj = ax ? (long long)j * n1 : (long long)j * n2;
-                x[u] = __ldcg(reinterpret_cast<const VT *>(S + o + si));
-                y[u] = __ldcg(reinterpret_cast<const VT *>(S + o + sj));
-            }
+        for (int u = 0; u < UNR; ++u) {
+            const bool ax = (off[u] >> 62) & 1;
+            const long long o = off[u] & ~(1LL << 62);
+            const long long si = ax ? (long long)i * n1 : (long long)i * n2, sj = ax ? (long long)j * n1 : (long long)j * n2;
+            x[u] = __ldcg(reinterpret_cast<const VT *>(S + o + si));
+            y[u] = __ldcg(reinterpret_cast<const VT *>(S + o + sj));
+        }
 #pragma unroll
         for (int u = 0; u < UNR; ++u)
-            if (off[u] >= 0) {
+            if (okmask & (1u << u)) {
                 const bool ax = (off[u] >> 62) & 1;
                 const long long o = off[u] & ~(1LL << 62);
                 const long long si = ax ? (long long)i * n1 : (long long)i * n2, sj = ax ? (long long)j * n1 : (long long)j * n2;
@@ -310,11 +326,93 @@ static __device__ __noinline__ void flat_update(double *__restrict__ S, const Wo
     }
 }
 
+// Dormant orbitals.  An orbital x that has not yet appeared in any super block of this launch cannot take part in a
+// rotation, so the flat phase skips every row pair whose free index is x: rows (i|j, x) of axis-1 rotations and rows
+// (x, i|j) of axis-2 rotations -- on average a third of the update traffic of a cycle.  What those rows missed is the
+// product R of all rotations so far acting on their other index; when x wakes up (three pairs before it is first
+// searched) the worker applies it in one go:
+//     S[a', y, x, d'] <- sum_{y'} R[y, y'] S[a', y', x, d'],    S[a', x, y, d'] <- sum_{y'} R[y, y'] S[a', x, y', d']
+// over the active orbitals y, y' (R is the identity outside them) for its owned columns.  Rg is the worker's private copy
+// of R in activation-rank coordinates (rows rank(i), rank(j) are rotated with every accepted pair).  Orbitals still
+// dormant at the end of the launch are caught up then.  One column per lane, one row y per warp, the row of R staged in
+// shared memory (prefetched one round ahead), the input vectors staged in shared memory first (the update is in place).
+static __device__ __noinline__ void catch_up(const Params &p, const WorkerSmem &sm, const double *Rg, double *cu_in, double *rowbuf,
+                                         int x, int A) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = p.n;
+    const long long n1 = n, n2 = n1 * n1;
+    constexpr int NWW = WORK_THREADS / 32;
+    double *myrow = rowbuf + (size_t)warp * n;
+    for (int o = 0; o < 2; ++o)
+        for (int c0 = 0; c0 < sm.ncd; c0 += CU_COLS) {
+            const int nc = min(CU_COLS, sm.ncd - c0);
+            // stage the input vectors: eight loads in flight per thread
+            for (int base = 0; base < A * CU_COLS; base += 8 * WORK_THREADS) {
+                double vv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = base + u * WORK_THREADS + tid, y = idx >> 5, c = idx & 31;
+                    vv[u] = 0.0;
+                    if (idx < A * CU_COLS && c < nc) {
+                        const int cc = c0 + c, oy = sm.alist[y];
+                        vv[u] = __ldcg(p.S + sm.piece[piece_of(sm, cc)].base + cc + (o == 0 ? oy * n2 + x * n1 : x * n2 + oy * n1));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = base + u * WORK_THREADS + tid;
+                    if (idx < A * CU_COLS) cu_in[idx] = vv[u];
+                }
+            }
+            named_sync<2, WORK_THREADS>();
+            double pre[CU_PRE];
+            const bool use_pre = A <= 32 * CU_PRE;
+            if (use_pre && warp < A) {
+#pragma unroll
+                for (int k = 0; k < CU_PRE; ++k)
+                    pre[k] = (lane + 32 * k < A) ? __ldcg(Rg + (size_t)warp * n + lane + 32 * k) : 0.0;
+            }
+            for (int y = warp; y < A; y += NWW) {
+                if (use_pre) {
+#pragma unroll
+                    for (int k = 0; k < CU_PRE; ++k)
+                        if (lane + 32 * k < A) myrow[lane + 32 * k] = pre[k];
+                    if (y + NWW < A) {
+#pragma unroll
+                        for (int k = 0; k < CU_PRE; ++k)
+                            pre[k] = (lane + 32 * k < A) ? __ldcg(Rg + (size_t)(y + NWW) * n + lane + 32 * k) : 0.0;
+                    }
+                } else {
+                    for (int k = lane; k < A; k += 32) myrow[k] = __ldcg(Rg + (size_t)y * n + k);
+                }
+                __syncwarp();
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int yp = 0;
+                for (; yp + 3 < A; yp += 4) {
+                    a0 += myrow[yp] * cu_in[yp * CU_COLS + lane];
+                    a1 += myrow[yp + 1] * cu_in[(yp + 1) * CU_COLS + lane];
+                    a2 += myrow[yp + 2] * cu_in[(yp + 2) * CU_COLS + lane];
+                    a3 += myrow[yp + 3] * cu_in[(yp + 3) * CU_COLS + lane];
+                }
+                for (; yp < A; ++yp) a0 += myrow[yp] * cu_in[yp * CU_COLS + lane];
+                a0 += a2;
+                a1 += a3;
+                if (lane < nc) {
+                    const int cc = c0 + lane, oy = sm.alist[y];
+                    double *dst = p.S + sm.piece[piece_of(sm, cc)].base + cc + (o == 0 ? oy * n2 + x * n1 : x * n2 + oy * n1);
+                    *dst = a0 + a1;
+                }
+                __syncwarp();
+            }
+            named_sync<2, WORK_THREADS>();
+        }
+}
+
 // One worker step: rotation (i, j, c, s) (if accepted) of the owned columns, producing the partial of super block `slot`
 // (if any) on the way.  Wg = the owned columns of W (private global copy, rotated here as well); Wr = shared-memory cache of
 // its rows E (the only ones a step reads), row t <-> orbital E[t].
 template <int V>
-__device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, double *Wg, double *Wr, int widx, int buf) {
+__device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, double *Wg, double *Wr, double *Rg, double *cu_in,
+                                            double *rowbuf, int widx, int buf) {
     using VT = typename std::conditional<V == 2, double2, double>::type;
     const int tid = threadIdx.x;
     const int n = p.n;
@@ -336,6 +434,18 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
             y = ny_;
         }
     };
+
+    // ---- orbitals that wake up in this step: apply what their rows missed (nothing before the first accepted rotation)
+    if (st.nnew > 0 && sm.any_rot)
+        for (int q = 0; q < st.nnew; ++q) catch_up(p, sm, Rg, cu_in, rowbuf, st.newc[q], st.na_before);
+    // ---- accumulated rotation: rows rank(i), rank(j) over the active columns (loads here, stores in w_consume)
+    const int nact = st.na_before + st.nnew, ri = rot ? sm.rank[i] : 0, rj = rot ? sm.rank[j] : 0;
+    double rx = 0.0, ry = 0.0;
+    const bool rrot = rot && tid < nact;
+    if (rrot) {
+        rx = __ldcg(Rg + (size_t)ri * n + tid);
+        ry = __ldcg(Rg + (size_t)rj * n + tid);
+    }
 
     // ---- W columns: rows E into shared memory, rows i, j rotated on the way (and written back).  The loads are issued
     // here and consumed after the tile pass has issued its own: one latency window for both.
@@ -364,6 +474,16 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
             Wr[col] = xn;
             Wr[pitch + col] = yn;
         };
+        if (rrot) {
+            Rg[(size_t)ri * n + tid] = c * rx + s * ry;
+            Rg[(size_t)rj * n + tid] = c * ry - s * rx;
+        }
+        if (rot)
+            for (int col = tid + TILE_THREADS; col < nact; col += TILE_THREADS) {
+                const double x = __ldcg(Rg + (size_t)ri * n + col), y = __ldcg(Rg + (size_t)rj * n + col);
+                Rg[(size_t)ri * n + col] = c * x + s * y;
+                Rg[(size_t)rj * n + col] = c * y - s * x;
+            }
         if (wrot) rot_col(tid, wx, wy);
         if (rot)
             for (int col = tid + TILE_THREADS; col < sm.ncols; col += TILE_THREADS)
@@ -534,17 +654,16 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
     if (widx == 0 && tid == 0) sm.t_tile += gtimer() - t_begin;
 
     // ---- flat phase: every other row pair of rotation (i, j) inside the owned columns ----------------------------
-    if (rot) flat_update<V>(p.S, &sm, sm.skipmask[buf], n, i, j, c, s, 0, 2LL * n * (sm.ncd / V), tid, WORK_THREADS);
+    if (rot) flat_update<V>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, tid, WORK_THREADS);
     if (tm2) sm.t_flat += gtimer() - t_b2;
 }
 
 // The planner warp of a worker: the plan of step w (rotation w, super block w + LOOK); w < 0: the prologue super blocks
-// 0 .. LOOK-1 from the initial state (no rotation).  `myE` = this lane's entry of the previous step's E (or -1).
-__device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm, int w, int &myE, int buf) {
+// 0 .. LOOK-1 from the initial state (no rotation).
+__device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm, int w, int buf) {
     WorkerStep &st = sm.st[buf];
     unsigned *skipmask = sm.skipmask[buf];
     const int lane = threadIdx.x & 31;
-    if (myE >= 0) skipmask[myE >> 5] = 0u;        // clear the skip bits of the step that used this buffer before
     int slot = w + LOOK;        // w = -3, -2, -1: super blocks 0, 1, 2 of the initial state
     // everything that depends on the pair list only comes first: it overlaps the wait for the angle
     int m = 0, Dq = -1;
@@ -554,6 +673,20 @@ __device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm
     } else {
         slot = -1;
     }
+    const bool has = lane < m;
+    // orbitals that appear in a super block for the first time wake up in this step
+    const bool isnew = has && sm.rank[Dq] < 0;
+    const unsigned newm = __ballot_sync(0xffffffffu, isnew);
+    const int na_before = sm.na_act, nnew = __popc(newm);
+    if (isnew) {
+        const int r = na_before + __popc(newm & ((1u << lane) - 1u));
+        sm.rank[Dq] = (short)r;
+        sm.alist[r] = (short)Dq;
+        st.newc[r - na_before] = Dq;
+        atomicAnd(&sm.dorm[Dq >> 5], ~(1u << (Dq & 31)));
+    }
+    __syncwarp();
+    skipmask[lane] = sm.dorm[lane];             // MAXN3 / 32 = 32 words: one per lane
     int i = 0, j = 0, acc = 0, alive = 1;
     double c = 1.0, s = 0.0;
     if (w >= 0) {
@@ -571,7 +704,6 @@ __device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm
     }
     __syncwarp();
     // E = [i, j] (if rotated) + the orbitals of D other than i, j, in the order of D
-    const bool has = lane < m;
     const bool isI = has && acc && Dq == i, isJ = has && acc && Dq == j, other = has && !isI && !isJ;
     const unsigned om = __ballot_sync(0xffffffffu, other);
     const int base = acc ? 2 : 0;
@@ -592,18 +724,47 @@ __device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm
         st.m = m;
         st.slot = slot;
         st.e = e;
+        st.nnew = nnew;
+        st.na_before = na_before;
+        sm.na_act = na_before + nnew;
         if (acc) {
             st.E[0] = i;
             st.E[1] = j;
         }
     }
     __syncwarp();
-    myE = lane < e ? st.E[lane] : -1;
+    const int myE = lane < e ? st.E[lane] : -1;
     if (myE >= 0) atomicOr(&skipmask[myE >> 5], 1u << (myE & 31));
+    __syncwarp();
+    // the rows the flat phase visits: active orbitals outside the tile, ascending (lane <-> one 32-bit word)
+    {
+        const int lo = 32 * lane, nn = p.n;
+        const unsigned valid = lo + 32 <= nn ? ~0u : (lo < nn ? ((1u << (nn - lo)) - 1u) : 0u);
+        unsigned bits = ~skipmask[lane] & valid;
+        const int cnt = __popc(bits);
+        int pos = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, pos, off);
+            if (lane >= off) pos += up;
+        }
+        const int total = __shfl_sync(0xffffffffu, pos, 31);
+        pos -= cnt;                                   // exclusive prefix
+        short *fl = sm.flatlist[buf];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            fl[pos++] = (short)(lo + b);
+        }
+        if (lane == 0) sm.nflat[buf] = total;
+    }
 }
 
 __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, double *Wr, int widx) {
     double *Wg = p.wg + (size_t)widx * p.n * p.wc_cols;
+    double *Rg = p.rg + (size_t)widx * p.n * p.n;
+    double *cu_in = Wr + (size_t)MAXE * p.wc_cols;            // [n][CU_COLS]
+    double *rowbuf = cu_in + (size_t)p.n * CU_COLS;            // [working warps][n]
     const int tid = threadIdx.x, n = p.n;
     // ---- owned columns: quanta [lo, hi) of the flat (slab, d / granule) space -------------------------------------
     if (tid == 0) {
@@ -627,8 +788,19 @@ __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, dou
         sm.npieces = np;
         sm.ncols = col;
     }
-    for (int k = tid; k < 256; k += THREADS) sm.skipmask[0][k] = 0u;
-    if (tid == 0) sm.t_tile = sm.t_wait = sm.t_pass = sm.t_flat = 0;
+    for (int k = tid; k < MAXN3 / 32; k += THREADS) {
+        const int lo = 32 * k;
+        sm.dorm[k] = lo + 32 <= n ? ~0u : (lo < n ? ((1u << (n - lo)) - 1u) : 0u);     // all orbitals dormant
+        sm.skipmask[0][k] = sm.skipmask[1][k] = 0u;
+    }
+    for (int k = tid; k < MAXN3; k += THREADS) sm.rank[k] = -1;
+    if (tid == 0) {
+        sm.t_tile = sm.t_wait = sm.t_pass = sm.t_flat = 0;
+        sm.na_act = 0;
+        sm.any_rot = 0;
+    }
+    // R = 1
+    for (int e = tid; e < n * n; e += THREADS) Rg[e] = (e / n == e % n) ? 1.0 : 0.0;
     __syncthreads();
     // this worker's columns of W into its private copy
     for (int pc = 0; pc < sm.npieces; ++pc) {
@@ -640,11 +812,10 @@ __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, dou
         for (int x = tid; x < n; x += THREADS) Wg[(size_t)x * p.wc_cols + P.slabcol] = __ldcg(p.W + (size_t)x * n + p.a0 + P.slab);
     }
     __syncthreads();
-    int myE[2] = {-1, -1};
     const bool timing = (widx == 0 && tid == 0);
     const bool planner = tid >= WORK_THREADS;
     unsigned long long t_plan = 0, t_step = 0, tq = timing ? gtimer() : 0;
-    if (planner) plan_worker_step(p, sm, -LOOK, myE[0], 0);
+    if (planner) plan_worker_step(p, sm, -LOOK, 0);
     __syncthreads();
     for (int w = -LOOK; w < p.P; ++w) {
         const int buf = (w + LOOK) & 1;
@@ -655,10 +826,11 @@ __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, dou
             tq = t;
         }
         if (planner) {
-            if (w + 1 < p.P) plan_worker_step(p, sm, w + 1, myE[buf ^ 1], buf ^ 1);     // overlaps step w
+            if (w + 1 < p.P) plan_worker_step(p, sm, w + 1, buf ^ 1);     // overlaps step w
         } else if (sm.st[buf].rotated || sm.st[buf].m > 0) {
-            if ((n & 1) == 0) worker_step<2>(p, sm, Wg, Wr, widx, buf);
-            else worker_step<1>(p, sm, Wg, Wr, widx, buf);
+            if ((n & 1) == 0) worker_step<2>(p, sm, Wg, Wr, Rg, cu_in, rowbuf, widx, buf);
+            else worker_step<1>(p, sm, Wg, Wr, Rg, cu_in, rowbuf, widx, buf);
+            if (tid == 0 && sm.st[buf].rotated) sm.any_rot = 1;
         }
         if (timing) {
             const unsigned long long t = gtimer();
@@ -666,6 +838,12 @@ __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, dou
             tq = t;
         }
         __syncthreads();
+    }
+    // orbitals that never appeared in a pair: their rows still miss every rotation of this launch
+    if (sm.any_rot && sm.na_act < n && !planner) {
+        const int A = sm.na_act;
+        for (int x = 0; x < n; ++x)
+            if (sm.rank[x] < 0) catch_up(p, sm, Rg, cu_in, rowbuf, x, A);
     }
     if (timing) {
         p.summary[16] = (double)t_plan;       // waiting at the step barrier (planner not ready / stragglers)
@@ -1075,7 +1253,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep3_kernel(Params p) {
 }
 
 struct Layout {
-    size_t off_ring, off_count, off_abort, off_tot, off_pbuf, off_dtab, off_wg, total;
+    size_t off_ring, off_count, off_abort, off_tot, off_pbuf, off_dtab, off_wg, off_rg, total;
 };
 static Layout ws_layout(int max_workers, int n) {
     Layout L;
@@ -1089,7 +1267,8 @@ static Layout ws_layout(int max_workers, int n) {
     L.off_wg = (L.off_wg + 255) / 256 * 256;
     // private W columns: every worker holds at most ceil(n^2 / workers') + MAX_PIECES columns (na <= n); bound with the
     // smallest worker count that can occur (Q >= workers) -- n (n + MAX_PIECES + 4) columns in total cover every case
-    L.total = L.off_wg + sizeof(double) * (size_t)n * ((size_t)n * n + (size_t)max_workers * (MAX_PIECES + 8));
+    L.off_rg = L.off_wg + sizeof(double) * (size_t)n * ((size_t)n * n + (size_t)max_workers * (MAX_PIECES + 8));
+    L.total = L.off_rg + sizeof(double) * (size_t)max_workers * n * n;       // private accumulated rotations
     return L;
 }
 
@@ -1103,7 +1282,7 @@ size_t sweep3_mailbox_bytes(int nranks) {
 // Shared memory of a worker for this problem, or 0 if the pipelined kernel cannot take it.
 static size_t worker_smem_bytes(int n, int na, int grid, int &nworkers, int &granule, int &wc_cols) {
     using namespace s3;
-    if (grid < FIRST_WORKER + 1 || n > 4096 || na < 1) return 0;
+    if (grid < FIRST_WORKER + 1 || n > MAXN3 || na < 1) return 0;
     granule = (n % 4 == 0) ? 4 : ((n % 2 == 0) ? 2 : 1);
     const long long qrow = n / granule, Q = (long long)na * qrow;
     nworkers = (int)std::min<long long>(grid - FIRST_WORKER, Q);
@@ -1113,7 +1292,7 @@ static size_t worker_smem_bytes(int n, int na, int grid, int &nworkers, int &gra
     if (pieces > MAX_PIECES) return 0;
     wc_cols = (int)(per * granule + pieces);
     wc_cols += (wc_cols & 1);      // even pitch
-    return ((sizeof(WorkerSmem) + 15) / 16) * 16 + sizeof(double) * (size_t)MAXE * wc_cols;
+    return ((sizeof(WorkerSmem) + 15) / 16) * 16 + sizeof(double) * ((size_t)MAXE * wc_cols + (size_t)n * CU_COLS + (size_t)(WORK_THREADS / 32) * n);
 }
 
 bool sweep3_supported(int n, int na) {
@@ -1156,7 +1335,8 @@ int sweep3_launch(double *gamma, double *S, double *U, double *W, int n, int a0,
     p.launch_id = ++launch_counter;
     p.dtab = reinterpret_cast<const int32_t *>(ws + L.off_dtab);
     p.wg = reinterpret_cast<double *>(ws + L.off_wg);
-    QIO_REQUIRE(L.off_wg + sizeof(double) * (size_t)p.nworkers * n * p.wc_cols <= L.total, "sweep_cycle: workspace too small for the private W columns");
+    p.rg = reinterpret_cast<double *>(ws + L.off_rg);
+    QIO_REQUIRE(L.off_wg + sizeof(double) * (size_t)p.nworkers * n * p.wc_cols <= L.off_rg, "sweep_cycle: workspace too small for the private W columns");
     p.rank = h_peers ? h_peers->rank : 0;
     p.nranks = h_peers ? h_peers->nranks : 1;
     p.epoch = h_peers ? (unsigned long long)h_peers->epoch : 0ull;
