@@ -381,7 +381,6 @@ def run_b200_arm(args):
     phases['sweep_phase_us_per_pair'] = sweep_phase_table(tsum, len(pairs_np))
     lsn = ['coarse', 'reduce', 'fine', 'scan', 'margin', 'tail']
     phases['linesearch_cycles_per_pair_cta0'] = {k: float(v) / len(pairs_np) for k, v in zip(lsn, tsum[10:16])}
-    phases['linesearch_cycles_per_pair_cta0'].update(dbg6=float(tsum[25]) / len(pairs_np), dbg7=float(tsum[26]) / len(pairs_np))
     algo_bytes = 16.0 * (n ** 4 - (n - 2) ** 4) * n_accepted      # bytes the reference update touches
     kernel_bytes = 64.0 * n ** 3 * n_accepted + 32.0 * n * n * len(pairs_np)   # what the deferred layout moves
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')

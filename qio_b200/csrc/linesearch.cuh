@@ -227,9 +227,7 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
         mg = warp_min_double(mg);
         if (lane == 0) sm.wmargin[warp] = mg;
     }
-    LS_PROF(6)
     ls_sync<NT>();
-    LS_PROF(7)
     double margin = INFINITY;
 #pragma unroll
     for (int w = 0; w < NW; ++w) margin = fmin(margin, sm.wmargin[w]);

@@ -1220,8 +1220,6 @@ __device__ __forceinline__ void search_main(const Params &p, SearchSmem &sm) {
         p.summary[8] = 0.0;
         p.summary[9] = (double)t_setup;       // T, contraction, coefficients
         for (int q = 0; q < 6; ++q) p.summary[10 + q] = (double)sm.ls.prof[q];
-        p.summary[25] = (double)sm.ls.prof[6];
-        p.summary[26] = (double)sm.ls.prof[7];
         p.summary[24] = 3.0;                  // engine id
     }
 }
