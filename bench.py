@@ -450,7 +450,8 @@ def sweep_phase_table(tsum, npairs):
         return {'engine': 3, 'cta0_wait_superblock': us(tsum[5]), 'cta0_setup_contract': us(tsum[9]), 'cta0_search': us(tsum[6]),
                 'cta0_publish': us(tsum[7]), 'worker0_wait_angle_plan': us(tsum[16]), 'worker0_step': us(tsum[17]),
                 'worker0_tile_phase': us(tsum[18]), 'worker0_pure_wait': us(tsum[19]), 'reducer0_wait': us(tsum[20]), 'reducer0_sum_publish': us(tsum[21]),
-                'worker0_tile_pass': us(tsum[22]), 'worker0_flat_thread128': us(tsum[23])}
+                'worker0_tile_pass': us(tsum[22]), 'worker0_flat_thread128': us(tsum[23]),
+                'worker0_t0_until_dots': us(tsum[25]), 'worker0_t0_dots': us(tsum[26]), 'worker0_t0_sync': us(tsum[27]), 'worker0_t0_post': us(tsum[28])}
     return {'engine': 2, 'cta0_gather': us(tsum[5]), 'cta0_search': us(tsum[6]), 'cta0_tail': us(tsum[7]), 'cta0_barrier_wait': us(tsum[8]),
             'cta1_superblock_orbits': us(tsum[16]), 'cta1_flat_update': us(tsum[17]), 'cta1_barrier_wait': us(tsum[18]),
             'flatcta_update': us(tsum[22]), 'flatcta_barrier_wait': us(tsum[23]),

@@ -56,7 +56,7 @@ constexpr int WORK_THREADS = THREADS - 32;   // a worker's warps 0..14 compute, 
 constexpr int TILE_THREADS = WORK_THREADS;   // all working warps do the tile phase, then the flat phase
 constexpr int MAXN3 = 1024;      // largest n of the pipelined kernel (rank / activation tables in shared memory)
 constexpr int CU_COLS = 32;       // columns per catch-up chunk (one per lane)
-constexpr int CU_PRE = 8;         // row prefetch registers of the catch-up (rows up to 256 entries)
+constexpr int CU_PITCH = 36;      // pitch of the staged catch-up vectors (conflict-free B fragments)
 constexpr int NRED = 4;          // reducer CTAs (each sums a quarter of the entries)
 constexpr unsigned long long TIMEOUT_NS = 4000000000ull;
 constexpr int AUX_CTA = NRED + 1;
@@ -112,6 +112,15 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
 __device__ __forceinline__ void red_release_add(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// asynchronous global -> shared copies (no registers, no stall at the issue): 16 bytes through L2, or 8 bytes
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int ID, int COUNT>
 __device__ __forceinline__ void named_sync() {
     asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
@@ -238,7 +247,7 @@ struct WorkerSmem {
     Piece piece[MAX_PIECES];
     int npieces, ncols, ncd;    // ncd = owned d-columns (concatenated over the pieces); ncols = ncd + npieces
     WorkerStep st[2];           // double-buffered: the planner warp writes step w + 1 while step w runs
-    unsigned long long t_tile, t_wait, t_pass, t_flat;
+    unsigned long long t_tile, t_wait, t_pass, t_flat, t_d[4];
     unsigned skipmask[2][MAXN3 / 32];   // bit x: the flat phase of that step leaves rows with index x alone (tile phase or dormant)
     unsigned dorm[MAXN3 / 32];  // planner: bit x = orbital x has not appeared in any super block of this launch yet
     short rank[MAXN3];          // activation rank of an orbital (-1: dormant); append-only
@@ -334,18 +343,22 @@ static __device__ __noinline__ void flat_update(double *__restrict__ S, const Wo
 //     S[a', y, x, d'] <- sum_{y'} R[y, y'] S[a', y', x, d'],    S[a', x, y, d'] <- sum_{y'} R[y, y'] S[a', x, y', d']
 // over the active orbitals y, y' (R is the identity outside them) for its owned columns.  Rg is the worker's private copy
 // of R in activation-rank coordinates (rows rank(i), rank(j) are rotated with every accepted pair).  Orbitals still
-// dormant at the end of the launch are caught up then.  One column per lane, one row y per warp, the row of R staged in
-// shared memory (prefetched one round ahead), the input vectors staged in shared memory first (the update is in place).
-static __device__ __noinline__ void catch_up(const Params &p, const WorkerSmem &sm, const double *Rg, double *cu_in, double *rowbuf,
-                                         int x, int A) {
+// dormant at the end of the launch are caught up then.  The input vectors are staged in shared memory first (the update is in place); the small GEMM runs on DMMA tiles.
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+static __device__ __noinline__ void catch_up(const Params &p, const WorkerSmem &sm, const double *Rg, double *cu_in, int x, int A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = p.n;
+    const int g = lane >> 2, t = lane & 3;
     const long long n1 = n, n2 = n1 * n1;
     constexpr int NWW = WORK_THREADS / 32;
-    double *myrow = rowbuf + (size_t)warp * n;
     for (int o = 0; o < 2; ++o)
         for (int c0 = 0; c0 < sm.ncd; c0 += CU_COLS) {
             const int nc = min(CU_COLS, sm.ncd - c0);
-            // stage the input vectors: eight loads in flight per thread
+            // stage the input vectors in[y][c] (pitch CU_PITCH): eight loads in flight per thread
             for (int base = 0; base < A * CU_COLS; base += 8 * WORK_THREADS) {
                 double vv[8];
 #pragma unroll
@@ -360,48 +373,43 @@ static __device__ __noinline__ void catch_up(const Params &p, const WorkerSmem &
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int idx = base + u * WORK_THREADS + tid;
-                    if (idx < A * CU_COLS) cu_in[idx] = vv[u];
+                    if (idx < A * CU_COLS) cu_in[(idx >> 5) * CU_PITCH + (idx & 31)] = vv[u];
                 }
             }
             named_sync<2, WORK_THREADS>();
-            double pre[CU_PRE];
-            const bool use_pre = A <= 32 * CU_PRE;
-            if (use_pre && warp < A) {
+            // out[8 rows of a warp][32 columns] = R[8 x A] in[A x 32] on the FP64 tensor pipe (m8n8k4): the A fragment
+            // (one element of R per lane) comes straight from L2 and is prefetched one k-step ahead, the B fragments from
+            // shared memory (pitch 36: conflict-free)
+            for (int y0 = 8 * warp; y0 < A; y0 += 8 * NWW) {
+                double acc[4][2];
 #pragma unroll
-                for (int k = 0; k < CU_PRE; ++k)
-                    pre[k] = (lane + 32 * k < A) ? __ldcg(Rg + (size_t)warp * n + lane + 32 * k) : 0.0;
-            }
-            for (int y = warp; y < A; y += NWW) {
-                if (use_pre) {
+                for (int ni = 0; ni < 4; ++ni) acc[ni][0] = acc[ni][1] = 0.0;
+                const bool rowok = y0 + g < A;
+                const double *rrow = Rg + (size_t)(y0 + g) * n + t;
+                double a_next = (rowok && t < A) ? __ldcg(rrow) : 0.0;
+                for (int k0 = 0; k0 < A; k0 += 4) {
+                    const double a = a_next;
+                    a_next = (rowok && k0 + 4 + t < A) ? __ldcg(rrow + k0 + 4) : 0.0;
+                    const bool kok = k0 + t < A;
 #pragma unroll
-                    for (int k = 0; k < CU_PRE; ++k)
-                        if (lane + 32 * k < A) myrow[lane + 32 * k] = pre[k];
-                    if (y + NWW < A) {
-#pragma unroll
-                        for (int k = 0; k < CU_PRE; ++k)
-                            pre[k] = (lane + 32 * k < A) ? __ldcg(Rg + (size_t)(y + NWW) * n + lane + 32 * k) : 0.0;
+                    for (int ni = 0; ni < 4; ++ni) {
+                        const double bb = kok ? cu_in[(k0 + t) * CU_PITCH + 8 * ni + g] : 0.0;
+                        dmma884(acc[ni][0], acc[ni][1], a, bb);
                     }
-                } else {
-                    for (int k = lane; k < A; k += 32) myrow[k] = __ldcg(Rg + (size_t)y * n + k);
                 }
-                __syncwarp();
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                int yp = 0;
-                for (; yp + 3 < A; yp += 4) {
-                    a0 += myrow[yp] * cu_in[yp * CU_COLS + lane];
-                    a1 += myrow[yp + 1] * cu_in[(yp + 1) * CU_COLS + lane];
-                    a2 += myrow[yp + 2] * cu_in[(yp + 2) * CU_COLS + lane];
-                    a3 += myrow[yp + 3] * cu_in[(yp + 3) * CU_COLS + lane];
+                if (rowok) {
+                    const int oy = sm.alist[y0 + g];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int c = 8 * ni + 2 * t + h;
+                            if (c < nc) {
+                                const int cc = c0 + c;
+                                p.S[sm.piece[piece_of(sm, cc)].base + cc + (o == 0 ? oy * n2 + x * n1 : x * n2 + oy * n1)] = acc[ni][h];
+                            }
+                        }
                 }
-                for (; yp < A; ++yp) a0 += myrow[yp] * cu_in[yp * CU_COLS + lane];
-                a0 += a2;
-                a1 += a3;
-                if (lane < nc) {
-                    const int cc = c0 + lane, oy = sm.alist[y];
-                    double *dst = p.S + sm.piece[piece_of(sm, cc)].base + cc + (o == 0 ? oy * n2 + x * n1 : x * n2 + oy * n1);
-                    *dst = a0 + a1;
-                }
-                __syncwarp();
             }
             named_sync<2, WORK_THREADS>();
         }
@@ -412,7 +420,7 @@ static __device__ __noinline__ void catch_up(const Params &p, const WorkerSmem &
 // its rows E (the only ones a step reads), row t <-> orbital E[t].
 template <int V>
 __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, double *Wg, double *Wr, double *Rg, double *cu_in,
-                                            double *rowbuf, int widx, int buf) {
+                                            int widx, int buf) {
     using VT = typename std::conditional<V == 2, double2, double>::type;
     const int tid = threadIdx.x;
     const int n = p.n;
@@ -437,7 +445,11 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
 
     // ---- orbitals that wake up in this step: apply what their rows missed (nothing before the first accepted rotation)
     if (st.nnew > 0 && sm.any_rot)
-        for (int q = 0; q < st.nnew; ++q) catch_up(p, sm, Rg, cu_in, rowbuf, st.newc[q], st.na_before);
+    {
+        const unsigned long long tc0 = (widx == 0 && tid == 0) ? gtimer() : 0;
+        for (int q = 0; q < st.nnew; ++q) catch_up(p, sm, Rg, cu_in, st.newc[q], st.na_before);
+        if (widx == 0 && tid == 0) sm.t_d[2] += gtimer() - tc0;
+    }
     // ---- accumulated rotation: rows rank(i), rank(j) over the active columns (loads here, stores in w_consume)
     const int nact = st.na_before + st.nnew, ri = rot ? sm.rank[i] : 0, rj = rot ? sm.rank[j] : 0;
     double rx = 0.0, ry = 0.0;
@@ -518,6 +530,15 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
             const int oa0 = st.E[ea0], ob0 = st.E[eb0];
             const int cc = t0 + v * V;
             double *g = p.S + sm.piece[piece_of(sm, cc)].base + cc + oa0 * n2 + ob0 * n1;
+            if (!two1 && !two2) {
+                // a row the rotation does not touch: only the dot products need it -- copied asynchronously, so that a
+                // thread's blocking (rotated) item and its untouched items share one latency window
+                if (m > 0) {
+                    VT *dst = reinterpret_cast<VT *>(sm.tile + (ea0 * e + eb0) * TILE_PITCH) + v;
+                    if constexpr (V == 2) cp_async_16(dst, g); else cp_async_8(dst, g);
+                }
+                continue;
+            }
             const long long dj1 = (long long)(j - oa0) * n2, dj2 = (long long)(j - ob0) * n1;   // to the partner rows
             VT q0, q1, q2, q3;      // rows (a, b), (a, j), (j, b), (j, j)
             q0 = __ldcg(reinterpret_cast<const VT *>(g));
@@ -549,6 +570,7 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
                 if (two1 && two2) *(reinterpret_cast<VT *>(sm.tile + (1 * e + 1) * TILE_PITCH) + v) = q3;
             }
         }
+        cp_async_wait_all();
     };
     // dot (piece, q, r, s) over the columns [t0, t0 + tl) of the tile; s varies fastest over the lanes (same tile element:
     // broadcast), the rows a warp reads sit on different banks (TILE_PITCH)
@@ -591,6 +613,9 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
             // four lanes per dot product (columns d = part mod 4), two shuffles, then the entries: all threads take part
             auto dots_quads = [&](auto mc) {
                 constexpr int M = decltype(mc)::value, M3 = M * M * M;
+                const bool tmd = (widx == 0 && tid == 0);
+                unsigned long long td = tmd ? gtimer() : 0;
+                if (tmd) sm.t_d[0] += td - t_begin;
                 for (int base = 0; base < ndot * 4; base += TILE_THREADS) {
                     const int idx4 = base + tid, idx = idx4 >> 2, part = idx4 & 3;
                     double acc = 0.0;
@@ -612,7 +637,9 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
                     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
                     if (part == 0 && idx < ndot) sm.dots[idx] = acc;
                 }
+                if (tmd) { const unsigned long long t = gtimer(); sm.t_d[1] += t - td; td = t; }
                 named_sync<2, TILE_THREADS>();
+                if (tmd) td = gtimer();
                 for (int en = tid; en < M * M3; en += TILE_THREADS) {
                     const int pp = en / M3, qrs = en - pp * M3;
                     const double *wrow = Wr + (size_t)st.tpos[pp] * pitch;
@@ -620,6 +647,7 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
                     for (int pc = 0; pc < sm.npieces; ++pc) acc += wrow[sm.piece[pc].slabcol] * sm.dots[pc * M3 + qrs];
                     ll_store(pslot + 2 * (size_t)en, (unsigned long long)__double_as_longlong(acc), ptag);
                 }
+                if (tmd) sm.t_d[3] += gtimer() - td;
             };
             switch (m) {
                 case 2: dots_quads(std::integral_constant<int, 2>{}); break;
@@ -763,8 +791,7 @@ __device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm
 __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, double *Wr, int widx) {
     double *Wg = p.wg + (size_t)widx * p.n * p.wc_cols;
     double *Rg = p.rg + (size_t)widx * p.n * p.n;
-    double *cu_in = Wr + (size_t)MAXE * p.wc_cols;            // [n][CU_COLS]
-    double *rowbuf = cu_in + (size_t)p.n * CU_COLS;            // [working warps][n]
+    double *cu_in = Wr + (size_t)MAXE * p.wc_cols;            // [n][CU_PITCH]
     const int tid = threadIdx.x, n = p.n;
     // ---- owned columns: quanta [lo, hi) of the flat (slab, d / granule) space -------------------------------------
     if (tid == 0) {
@@ -796,6 +823,7 @@ __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, dou
     for (int k = tid; k < MAXN3; k += THREADS) sm.rank[k] = -1;
     if (tid == 0) {
         sm.t_tile = sm.t_wait = sm.t_pass = sm.t_flat = 0;
+        sm.t_d[0] = sm.t_d[1] = sm.t_d[2] = sm.t_d[3] = 0;
         sm.na_act = 0;
         sm.any_rot = 0;
     }
@@ -828,8 +856,8 @@ __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, dou
         if (planner) {
             if (w + 1 < p.P) plan_worker_step(p, sm, w + 1, buf ^ 1);     // overlaps step w
         } else if (sm.st[buf].rotated || sm.st[buf].m > 0) {
-            if ((n & 1) == 0) worker_step<2>(p, sm, Wg, Wr, Rg, cu_in, rowbuf, widx, buf);
-            else worker_step<1>(p, sm, Wg, Wr, Rg, cu_in, rowbuf, widx, buf);
+            if ((n & 1) == 0) worker_step<2>(p, sm, Wg, Wr, Rg, cu_in, widx, buf);
+            else worker_step<1>(p, sm, Wg, Wr, Rg, cu_in, widx, buf);
             if (tid == 0 && sm.st[buf].rotated) sm.any_rot = 1;
         }
         if (timing) {
@@ -843,7 +871,7 @@ __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, dou
     if (sm.any_rot && sm.na_act < n && !planner) {
         const int A = sm.na_act;
         for (int x = 0; x < n; ++x)
-            if (sm.rank[x] < 0) catch_up(p, sm, Rg, cu_in, rowbuf, x, A);
+            if (sm.rank[x] < 0) catch_up(p, sm, Rg, cu_in, x, A);
     }
     if (timing) {
         p.summary[16] = (double)t_plan;       // waiting at the step barrier (planner not ready / stragglers)
@@ -851,7 +879,8 @@ __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, dou
         p.summary[18] = (double)sm.t_tile;    // tile phase (incl. partial post) of worker 0
         p.summary[19] = (double)sm.t_wait;    // of [16]: inside the wait for the angle record
         p.summary[22] = (double)sm.t_pass;    // tile pass (global loads, rotation, stores) up to the CTA barrier, thread 128
-        p.summary[23] = (double)sm.t_flat;    // flat phase as seen by thread 128 (not a dot-product thread)
+        p.summary[23] = (double)sm.t_flat;
+        for (int q = 0; q < 4; ++q) p.summary[25 + q] = (double)sm.t_d[q];    // flat phase as seen by thread 128 (not a dot-product thread)
     }
 }
 
@@ -1290,7 +1319,7 @@ static size_t worker_smem_bytes(int n, int na, int grid, int &nworkers, int &gra
     if (pieces > MAX_PIECES) return 0;
     wc_cols = (int)(per * granule + pieces);
     wc_cols += (wc_cols & 1);      // even pitch
-    return ((sizeof(WorkerSmem) + 15) / 16) * 16 + sizeof(double) * ((size_t)MAXE * wc_cols + (size_t)n * CU_COLS + (size_t)(WORK_THREADS / 32) * n);
+    return ((sizeof(WorkerSmem) + 15) / 16) * 16 + sizeof(double) * ((size_t)MAXE * wc_cols + (size_t)n * CU_PITCH);
 }
 
 bool sweep3_supported(int n, int na) {
