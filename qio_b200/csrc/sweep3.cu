@@ -16,14 +16,17 @@
 //  * Roles.  CTA 0 searches (320 threads) and prefetches the next super block (192 threads).  CTAs 1..4 reduce the workers'
 //    partial super blocks in a fixed order and publish the total (to every rank's mailbox when sharded).  CTA 5 keeps the
 //    small replicated state (gamma, U, W) and publishes the gamma part of the super block.  CTAs 6.. are workers: wait for
-//    angle w -> rotate the rows of the next super block (P_{w+3}) inside their columns, take the dot products with their
-//    columns of W (kept in shared memory, rotated locally) -> post the partial -> stream the rest of rotation w.
-//  * Signalling is one-directional and tagged: angle records and totals are 16-byte (value, tag) words written with a
-//    single store and polled by the consumer ("LL" style), partial arrivals are a monotone counter.  Slot counts follow from
-//    how far the parties can drift apart (see the constants).  Every wait has a time-out that aborts the whole kernel.
+//    angle w (warp 15 polls it one step ahead and prepares the step's plan) -> rotate the rows of the next super block
+//    (P_{w+3}) inside their columns, take the dot products with their columns of W (private global copy, the rows a step
+//    needs cached in shared memory and rotated locally) -> post the partial -> stream the rest of rotation w.
+//  * Dormant orbitals: rows of orbitals that have not yet appeared in any super block are skipped by the update and caught
+//    up with the accumulated rotation when they wake (see catch_up).
+//  * Signalling is one-directional and tagged: angle records, partials and totals are 16-byte (value, tag) words written
+//    with a single store and polled by the consumer ("LL" style).  Slot counts follow from how far the parties can drift
+//    apart (see the constants).  Every wait has a time-out that aborts the whole kernel (summary[3]).
 //
-// The launch is cooperative only to guarantee that all CTAs are co-resident.  Cases whose W columns do not fit in shared
-// memory (n = 200 on one GPU) stay on the barrier kernel of sweep2.cu (see qio_b200_sweep_cycle).
+// The launch is cooperative only to guarantee that all CTAs are co-resident.  n > 1024, or shapes where a worker would own
+// more than four row pieces, stay on the barrier kernel of sweep2.cu (see qio_b200_sweep_cycle).
 #include <string.h>
 
 #include <algorithm>
