@@ -339,7 +339,7 @@ def test_deferred_engine_matches_materialized_engine(n):
     assert abs(get_cost_fqi(b[4], b[5], inact) - b[3]) < 1e-12
 
 
-@pytest.mark.parametrize('n,K', [(6, 3), (6, 7), (12, 5), (12, 30), (13, 9), (28, 40)])
+@pytest.mark.parametrize('n,K', [(6, 1), (6, 2), (6, 3), (6, 7), (12, 5), (12, 30), (13, 9), (28, 40)])
 def test_partial_pair_list_pipelined_matches_barrier_kernel(n, K):
     """A launch that visits only the first K pairs leaves orbitals that never entered a pair ("dormant" in the
     pipelined kernel: their rows are skipped by the update and caught up at the end of the launch).  Both sweep
@@ -365,7 +365,7 @@ def test_partial_pair_list_pipelined_matches_barrier_kernel(n, K):
     a, b = out['3'], out['2']
     assert np.array_equal(a[0]['accepted'], b[0]['accepted'])
     assert np.array_equal(a[0]['theta'], b[0]['theta'], equal_nan=True)
-    assert a[0]['accepted'].sum() > 0
+    assert K < 3 or a[0]['accepted'].sum() > 0
     for k in (1, 2, 3, 4):
         assert np.allclose(a[k], b[k], atol=1e-12, rtol=0)
 
