@@ -369,6 +369,17 @@ def run_b200_arm(args):
                                                 dev.results_to_numpy(state['ls_all'])['coarse_index'], 0)]).sum())
     phases['all_pairs_evals_per_s'] = m1_evals / (phases['linesearch_all_pairs_ms'] * 1e-3)
 
+    # one Newton-Raphson ("nr", the path of the reference's examples) iteration through the public API, device-resident
+    # RDMs: grad/Hess kernels, D2H of two n x n matrices, host level shift + scipy expm, H2D of U, 4-index rotation, cost
+    from qio_b200.grad import gradient as GR
+    dev.prep_rdm12(dm1_d, dm2_d, n, gamma=gamma, Gamma=Gamma)
+    GR.minimize_orb_corr_GD(gamma, Gamma, inact, np.zeros(0, dtype=np.int64), max_cycle=1, thresh=0.0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    GR.minimize_orb_corr_GD(gamma, Gamma, inact, np.zeros(0, dtype=np.int64), max_cycle=4, thresh=0.0)
+    torch.cuda.synchronize()
+    phases['gd_newton_iteration_ms'] = (time.perf_counter() - t0) * 1e3 / 4
+
     # dominant kernel = the persistent sweep kernel.  Timed alone on the step's own first cycle (same start state).
     dev.prep_rdm12(dm1_d, dm2_d, n, gamma=gamma, Gamma=Gamma)
     g = dev.rotate_rdm1(U0_d, gamma, n)
