@@ -129,7 +129,7 @@ extern "C" int qio_b200_pair_entropy(const double *blocks, const double *supp, i
     QIO_REQUIRE(P >= 0, "pair_entropy: bad size");
     if (P == 0) return QIO_B200_OK;
     QIO_REQUIRE(blocks && s_pair, "pair_entropy: NULL pointer");
-    pair_entropy_kernel<<<(P + 127) / 128, 128, 0, as_stream(stream)>>>(blocks, supp, P, s_pair, eig, flags);
+    pair_entropy_kernel<<<(P + 31) / 32, 32, 0, as_stream(stream)>>>(blocks, supp, P, s_pair, eig, flags);      // >= one CTA per SM from ~4,700 pairs on
     QIO_LAUNCH_CHECK();
     return QIO_B200_OK;
 }

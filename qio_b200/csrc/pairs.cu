@@ -48,7 +48,7 @@ __device__ __forceinline__ void stage_records(const double *__restrict__ blocks,
 }
 
 // ---- all-pairs gradient / Hessian ------------------------------------------------------------
-constexpr int GH_THREADS = 128;
+constexpr int GH_THREADS = 32;        // one pair per thread; small CTAs so that 4,950 pairs already give more CTAs than SMs
 
 __device__ __forceinline__ void pair_from_linear(long long k, int &i, int &j) {
     // k = i(i-1)/2 + j, 0 <= j < i   (row-major lower triangle, the order of gradient.py:128-130)
