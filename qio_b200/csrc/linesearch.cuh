@@ -59,12 +59,17 @@ struct LineSearchSmemT {
 };
 using LineSearchSmem = LineSearchSmemT<LS_THREADS>;
 
+// stage timers of thread 0 (cycles): only in translation units that define QIO_LS_TIMED (the timed sweep kernels)
+#ifdef QIO_LS_TIMED
 #define LS_PROF(k)                                  \
     if (tid == 0) {                                 \
         const long long now_ = clock64();           \
         sm.prof[k] += now_ - sm.prof_last;          \
         sm.prof_last = now_;                        \
     }
+#else
+#define LS_PROF(k)
+#endif
 
 template <int NT>
 __device__ __forceinline__ void ls_sync() {

@@ -31,6 +31,7 @@
 
 #include <stdlib.h>
 
+#define QIO_LS_TIMED 1      // this kernel reports the line-search stage timers in its summary
 #include "linesearch.cuh"
 #include "sweep3.cuh"
 
