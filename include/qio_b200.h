@@ -182,10 +182,14 @@ int qio_b200_contract_axis_partial(const double *U, long long ldu, const double 
  * slabs S[a0 : a0+na] of the (deferred) leading axis; gamma, U, W are replicated on every rank.
  * sweep_reset sets W = 1 (S = Gamma then).  sweep_cycle runs the pair sequence exactly like
  * qio_b200_jacobi_cycle (same result records) but touches only 64 n^3 B of S per accepted rotation, all
- * row-contiguous and shard-local, and searches pair t+1 while pair t is being applied.  With peers, every
- * rank calls it with the same arguments on its own shard; 256 doubles per pair are exchanged through
- * peer-mapped mailboxes inside the kernel (no NCCL call on the path) and all ranks take identical decisions.
- * summary (16) = [number accepted, unused, OR of flags, 0, then six phase timers of CTA 0 in ns, rest 0].
+ * row-contiguous and shard-local, and searches ahead of the pair being applied.  With peers, every
+ * rank calls it with the same arguments on its own shard; one small super block (256 doubles in a run of pairs that
+ * share an orbital, at most 1296) per pair is exchanged through peer-mapped mailboxes inside the kernel (no NCCL call
+ * on the path) and all ranks take identical decisions.
+ * summary (32 doubles) = [0] number accepted, [2] OR of flags, [3] != 0: a wait inside the pipelined kernel timed out
+ * (cycle incomplete), [24] engine (3 = pipelined, 0 = barrier kernel); the other entries are phase timers in ns
+ * (line-search stages in SM cycles), filled by the barrier kernel always and by the pipelined kernel only when
+ * QIO_B200_SWEEP_TIMERS is set in the environment (a second build of the kernel that carries the timers).
  * deferred_diagonals is orbital_diagonals through the pending W (per-shard partial sums).  To obtain Gamma
  * again: contract_axis(W, S -> work, leading) then contract_axis(W, work -> S, last), then sweep_reset. */
 typedef struct qio_b200_peers {
