@@ -36,7 +36,7 @@ extern "C" {
 #define QIO_B200_ERR_CUDA (-2)
 #define QIO_B200_ERR_UNSUPPORTED (-3)
 
-#define QIO_B200_ABI_VERSION 1
+#define QIO_B200_ABI_VERSION 2
 
 /* pair-block record: 16 Gamma entries Gamma[I_m, I_n, I_p, I_q] (I = (i, j), index m*8+n*4+p*2+q),
  * then gamma_up 2x2 (row-major over (I_m, I_n)), then gamma_dn 2x2. */
@@ -163,6 +163,12 @@ int qio_b200_rotate_rdm2(const double *U, double *Gamma, double *work, int n, vo
  * the sharded rotation (the caller re-shards between passes). */
 int qio_b200_rotate_axis(const double *U, const double *in, double *out, int n, long long rows,
                          long long ld_in, void *stream);
+/* `batch` such passes in ONE launch: problem b reads in + b * batch_stride_in, writes out + b * batch_stride_out
+ * (strides in doubles).  The local slabs of a leading-index shard are rotated on their trailing axes this way
+ * (rows = n^2, ld_in = n^2, strides n^3): three launches per shard instead of three per slab. */
+int qio_b200_rotate_axis_batched(const double *U, const double *in, double *out, int n, long long rows,
+                                 long long ld_in, int batch, long long batch_stride_in, long long batch_stride_out,
+                                 void *stream);
 
 /* Single-axis contraction that keeps the index order (used to flush the deferred sweep state):
  *   last_axis == 0:  out[i, m] = sum_a U[i, a] in[a, m]   in, out are (n, rows)
@@ -189,38 +195,64 @@ int qio_b200_contract_axis_partial(const double *U, long long ldu, const double 
  * summary (32 doubles) = [0] number accepted, [2] OR of flags, [3] != 0: a wait inside the pipelined kernel timed out
  * (cycle incomplete), [24] engine (3 = pipelined, 0 = barrier kernel); the other entries are phase timers in ns
  * (line-search stages in SM cycles), filled by the barrier kernel always and by the pipelined kernel only when
- * QIO_B200_SWEEP_TIMERS is set in the environment (a second build of the kernel that carries the timers).
+ * options.timers is set (a second build of the kernel that carries the timers).
  * deferred_diagonals is orbital_diagonals through the pending W (per-shard partial sums).  To obtain Gamma
- * again: contract_axis(W, S -> work, leading) then contract_axis(W, work -> S, last), then sweep_reset. */
+ * again: contract_axis(W, S -> work, leading) then contract_axis(W, work -> S, last), then sweep_reset.
+ * The library keeps NO state between calls: everything that selects a code path travels in qio_b200_sweep_options,
+ * everything that distinguishes launches (the mailbox epoch) in qio_b200_peers, and the signalling words of the
+ * workspace are cleared by every launch. */
 typedef struct qio_b200_peers {
     int32_t rank, nranks;
-    uint32_t epoch;         /* must differ between consecutive sweep_cycle calls and agree on all ranks */
+    uint32_t epoch;         /* 1..4095; must differ between consecutive sweep_cycle calls and agree on all ranks; before
+                               a value is reused every rank must have zeroed its own mailbox behind a barrier */
     uint32_t reserved;
     void *const *mailboxes; /* DEVICE array [nranks] of mailbox base pointers as mapped into THIS process
                                (own + cudaIpc-opened peers); each mailbox has qio_b200_mailbox_bytes(nranks) */
 } qio_b200_peers;
+/* Options of one sweep_cycle call (host struct; NULL = all defaults). */
+typedef struct qio_b200_sweep_options {
+    int32_t engine;              /* 0 = automatic (qio_b200_sweep_engine), 2 = barrier kernel, 3 = pipelined kernel
+                                    (QIO_B200_ERR_UNSUPPORTED when the shape does not fit it) */
+    int32_t timers;              /* != 0: the build of the pipelined kernel that carries its phase timers (~5 % slower) */
+    uint32_t timeout_ms;         /* time-out of every wait inside the pipelined kernel; 0 = 4000 */
+    uint32_t startup_timeout_ms; /* the same until the first super block has arrived (launch skew between ranks,
+                                    lazy module loading, an attached profiler); 0 = 60000 */
+    double *blocks_out;          /* DEVICE (P, QIO_B200_BLOCK_DOUBLES) or NULL: the pair block every line search of the
+                                    cycle ran on -- feeding it to qio_b200_pair_linesearch(strict_order = 1) re-derives
+                                    every decision of the cycle in the reference's own operation order (decision audit) */
+} qio_b200_sweep_options;
 size_t qio_b200_sweep_workspace_bytes(int n);
-/* Which kernel sweep_cycle runs for (n, na): 3 = pipelined (no grid barriers: column-owning worker CTAs, a reducer CTA and a
- * search CTA that works three rotations ahead of the data it needs; used wherever a worker's columns of W fit in shared
- * memory), 2 = one grid barrier per pair.  Same results records either way.  QIO_B200_SWEEP_ENGINE=2 forces the latter.
- * summary[3] != 0 reports that a wait inside the pipelined kernel timed out (the cycle is then incomplete). */
+/* Which kernel sweep_cycle runs by default for (n, na): 3 = pipelined (no grid barriers: column-owning worker CTAs, reducer
+ * CTAs and a search CTA that works three rotations ahead of the data it needs; used wherever a worker's columns of W fit in
+ * shared memory), 2 = one grid barrier per pair.  Same result records either way. */
 int qio_b200_sweep_engine(int n, int na);
 size_t qio_b200_mailbox_bytes(int nranks);
 int qio_b200_sweep_reset(double *W, int n, void *stream);
 int qio_b200_sweep_cycle(double *gamma, double *S, double *U, double *W, int n, int a0, int na,
                          const int32_t *pairs, int P, const int32_t *inactive,
                          const qio_b200_theta_tables *h_tables, qio_b200_ls_result *results, double *summary,
-                         void *workspace, const qio_b200_peers *h_peers, void *stream);
+                         void *workspace, const qio_b200_peers *h_peers, const qio_b200_sweep_options *h_opts,
+                         void *stream);
 int qio_b200_deferred_diagonals(const double *gamma, const double *S, const double *W, int n, int a0, int na,
                                 const int32_t *inds, int m, double *diag, void *stream);
 /* zeroes the up-down / down-up entries of gamma when summary[0] > 0 (the reference's jacobi_transform
  * returns zeros there, qio/grad/jacobi.py:87). */
 int qio_b200_zero_offspin_if_rotated(double *gamma, int n, const double *summary, void *stream);
-/* cudaMalloc'ed, zeroed buffer + its 64-byte CUDA IPC handle; open / close a peer's; free one's own. */
+/* cudaMalloc'ed, zeroed buffer + its 64-byte CUDA IPC handle; open / close a peer's; free one's own; clear zeroes
+ * one's own mailbox again (stream-ordered) -- required, between two barriers over the ranks, before an epoch is reused. */
 int qio_b200_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle64);
+int qio_b200_ipc_clear(void *ptr, size_t bytes, void *stream);
 int qio_b200_ipc_open(const unsigned char *handle64, void **ptr);
 int qio_b200_ipc_close(void *ptr);
 int qio_b200_ipc_free(void *ptr);
+/* Self-test of the tagged-word signalling over the peer mailboxes (which must hold at least
+ * max(qio_b200_mailbox_bytes, qio_b200_ll_stress_bytes) bytes): `iterations` rounds in which every rank stores `lanes`
+ * (<= 256) tagged 16-byte words into every rank's mailbox and verifies every payload bit of the words it receives.
+ * All ranks call it together with the same arguments and a fresh epoch.  result (device, 3 x uint64) = [payload
+ * mismatches (torn or stale words that passed the tag check), time-outs, words checked]. */
+size_t qio_b200_ll_stress_bytes(int nranks);
+int qio_b200_ll_stress(const qio_b200_peers *h_peers, int iterations, int lanes, unsigned long long *result,
+                       void *stream);
 
 /* ---- a-7  qio/grad/jacobi.py:211-233  one Jacobi cycle over a given pair sequence ------------
  * For each pair in order: line search on the CURRENT RDMs, and when an angle is accepted the
@@ -243,6 +275,10 @@ int qio_b200_jacobi_cycle(double *gamma, double *Gamma, double *U, int n, const 
 #define QIO_B200_MI_SUPP_DOUBLES 9
 int qio_b200_pair_entropy(const double *blocks, const double *supp, int P, double *s_pair,
                           double *eig, int32_t *flags, void *stream);
+/* Mutual-information matrix I (n, n): I[i,j] = I[j,i] = s1[i] + s1[j] - s_pair[p] for pairs[p] = (i, j); zero diagonal.
+ * s1 (n) = one-orbital entropies (qio_b200_orbital_entropies, s_masked), s_pair (P) from qio_b200_pair_entropy. */
+int qio_b200_mutual_information(const double *s1, const double *s_pair, const int32_t *pairs, int P, int n,
+                                double *I, void *stream);
 
 #ifdef __cplusplus
 }

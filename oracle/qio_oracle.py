@@ -318,6 +318,23 @@ def jacobi_transform(gamma, Gamma, i, j, t):
     return g, G
 
 
+def jacobi_transform_inplace(gamma, Gamma, i, j, t):
+    """jacobi_transform with Gamma updated IN PLACE (same arithmetic, no 8 n^4-byte copy per call): what the headline-size
+    prefix tests use (n = 100: 0.8 GB per copy).  Returns (fresh gamma, the same Gamma array)."""
+    n = Gamma.shape[0]
+    c, s = np.cos(t), np.sin(t)
+    for axis in range(4):
+        G = np.moveaxis(Gamma, axis, 0)             # a view: the assignments below write into Gamma
+        gi, gj = G[i].copy(), G[j].copy()
+        G[i] = c * gi + s * gj
+        G[j] = -s * gi + c * gj
+    V = givens_matrix(n, i, j, t)
+    g = np.zeros((2 * n, 2 * n))
+    for spin in (0, 1):
+        g[spin::2, spin::2] = V @ gamma[spin::2, spin::2] @ V.T
+    return g, Gamma
+
+
 def jacobi_transform_dense(gamma, Gamma, i, j, t):
     """Same as jacobi_transform but through the dense 4-index contraction the reference
     actually executes (jacobi.py:90) -- what the CPU baseline times."""

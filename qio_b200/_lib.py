@@ -39,6 +39,12 @@ class ThetaTables(ctypes.Structure):
                 ('fine_cs', ctypes.c_void_p)]
 
 
+class SweepOptions(ctypes.Structure):
+    """struct qio_b200_sweep_options (all zero = defaults)"""
+    _fields_ = [('engine', ctypes.c_int32), ('timers', ctypes.c_int32), ('timeout_ms', ctypes.c_uint32),
+                ('startup_timeout_ms', ctypes.c_uint32), ('blocks_out', ctypes.c_void_p)]
+
+
 class Peers(ctypes.Structure):
     """struct qio_b200_peers"""
     _fields_ = [('rank', ctypes.c_int32), ('nranks', ctypes.c_int32), ('epoch', ctypes.c_uint32),
@@ -75,6 +81,7 @@ SIGNATURES = {
     'qio_b200_rotate_rdm1': ([_p, _p, _p, _i, _p], _i),
     'qio_b200_rotate_rdm2': ([_p, _p, _p, _i, _p], _i),
     'qio_b200_rotate_axis': ([_p, _p, _p, _i, _ll, _ll, _p], _i),
+    'qio_b200_rotate_axis_batched': ([_p, _p, _p, _i, _ll, _ll, _i, _ll, _ll, _p], _i),
     'qio_b200_contract_axis': ([_p, _p, _p, _i, _ll, _i, _p], _i),
     'qio_b200_contract_axis_partial': ([_p, _ll, _p, _p, _i, _i, _ll, _p], _i),
     'qio_b200_sweep_workspace_bytes': ([_i], ctypes.c_size_t),
@@ -82,14 +89,18 @@ SIGNATURES = {
     'qio_b200_sweep_reset': ([_p, _i, _p], _i),
     'qio_b200_mailbox_bytes': ([_i], ctypes.c_size_t),
     'qio_b200_sweep_cycle': ([_p, _p, _p, _p, _i, _i, _i, _p, _i, _p, ctypes.POINTER(ThetaTables), _p, _p, _p,
-                              ctypes.POINTER(Peers), _p], _i),
+                              ctypes.POINTER(Peers), ctypes.POINTER(SweepOptions), _p], _i),
     'qio_b200_deferred_diagonals': ([_p, _p, _p, _i, _i, _i, _p, _i, _p, _p], _i),
     'qio_b200_ipc_alloc': ([ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p], _i),
     'qio_b200_ipc_open': ([ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)], _i),
     'qio_b200_ipc_close': ([_p], _i),
     'qio_b200_ipc_free': ([_p], _i),
+    'qio_b200_ipc_clear': ([_p, ctypes.c_size_t, _p], _i),
+    'qio_b200_ll_stress_bytes': ([_i], ctypes.c_size_t),
+    'qio_b200_ll_stress': ([ctypes.POINTER(Peers), _i, _i, _p, _p], _i),
     'qio_b200_zero_offspin_if_rotated': ([_p, _i, _p, _p], _i),
     'qio_b200_pair_entropy': ([_p, _p, _i, _p, _p, _p, _p], _i),
+    'qio_b200_mutual_information': ([_p, _p, _p, _i, _i, _p, _p], _i),
     'qio_b200_jacobi_workspace_bytes': ([_i, _i], ctypes.c_size_t),
     'qio_b200_jacobi_cycle': ([_p, _p, _p, _i, _p, _i, _p, ctypes.POINTER(ThetaTables), _p, _p, _p, _p], _i),
 }

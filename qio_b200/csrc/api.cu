@@ -20,16 +20,12 @@ int arg_fail(const char *msg) {
 }
 
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-            cached = sms;
-        else
-            return 148;
-    }
-    return cached;
+    // queried per call for the CURRENT device: no process-wide cache (the attribute query costs well under a microsecond)
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+        return sms;
+    return 148;
 }
 
 }  // namespace qio

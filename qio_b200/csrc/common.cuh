@@ -32,6 +32,6 @@ int arg_fail(const char *msg);
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
-int sm_count();  // cached multiprocessor count of the current device (148 on B200)
+int sm_count();  // multiprocessor count of the current device (148 on B200); queried per call, nothing cached
 
 }  // namespace qio

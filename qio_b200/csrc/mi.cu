@@ -121,7 +121,31 @@ __global__ void __launch_bounds__(128)
     if (flags) flags[p] = mn < -1e-6 ? QIO_B200_FLAG_WARN_NEGATIVE : 0;
 }
 
+// I[i, j] = I[j, i] = S_i + S_j - S_ij for the listed pairs (the matrix is zeroed first: zero diagonal, zero for pairs not listed)
+__global__ void __launch_bounds__(256)
+    mi_matrix_kernel(const double *__restrict__ s1, const double *__restrict__ s_pair, const int32_t *__restrict__ pairs, int P,
+                     int n, double *__restrict__ I) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int i = pairs[2 * p], j = pairs[2 * p + 1];
+    const double v = s1[i] + s1[j] - s_pair[p];
+    I[(size_t)i * n + j] = v;
+    I[(size_t)j * n + i] = v;
+}
+
 }  // namespace qio
+
+extern "C" int qio_b200_mutual_information(const double *s1, const double *s_pair, const int32_t *pairs, int P, int n,
+                                           double *I, void *stream) {
+    using namespace qio;
+    QIO_REQUIRE(P >= 0 && n > 0 && I, "mutual_information: bad arguments");
+    QIO_CUDA(cudaMemsetAsync(I, 0, sizeof(double) * (size_t)n * n, as_stream(stream)));
+    if (P == 0) return QIO_B200_OK;
+    QIO_REQUIRE(s1 && s_pair && pairs, "mutual_information: NULL pointer");
+    mi_matrix_kernel<<<(P + 255) / 256, 256, 0, as_stream(stream)>>>(s1, s_pair, pairs, P, n, I);
+    QIO_LAUNCH_CHECK();
+    return QIO_B200_OK;
+}
 
 extern "C" int qio_b200_pair_entropy(const double *blocks, const double *supp, int P, double *s_pair, double *eig,
                                      int32_t *flags, void *stream) {

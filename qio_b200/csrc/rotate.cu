@@ -14,7 +14,6 @@
 // Tiling: CTA = 128 (M) x 16*NT8 (N), 8 warps as 4 (M) x 2 (N), warp tile 32 x 8*NT8, K in slabs
 // of 16 through a 4-stage cp.async pipeline.  Shared-memory pitches (132 / 20 doubles) make all
 // fragment loads bank-conflict free.
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -22,7 +21,7 @@ namespace qio {
 
 // rotate_tma.cu: persistent TMA-fed kernel for MODE_CYCLIC / MODE_LEAD_KEEP; returns 1 if it ran, 0 if not eligible
 int rotate_axis_tma(const double *U, const double *in, double *out, int n, int kdim, long long ldu, long long rows,
-                    long long ld_in, long long ld_out, bool lead_keep, cudaStream_t st);
+                    long long ld_in, long long ld_out, bool lead_keep, int batch, long long bs_in, long long bs_out, cudaStream_t st);
 
 constexpr int RA_BM = 128;
 constexpr int RA_BK = 16;
@@ -217,12 +216,8 @@ template <int MODE>
 static int dispatch_rotate_axis(const double *U, const double *in, double *out, int n, int kdim, long long ldu,
                                 long long rows, long long ld_in, long long ld_out, cudaStream_t st) {
     if (MODE != MODE_LAST) {
-        // QIO_B200_ROTATE=cpasync keeps the cp.async kernel of this file (A/B comparison)
-        const char *e = getenv("QIO_B200_ROTATE");
-        if (!(e && e[0] == 'c')) {
-            const int rc = rotate_axis_tma(U, in, out, n, kdim, ldu, rows, ld_in, ld_out, MODE == MODE_LEAD_KEEP, st);
-            if (rc != 0) return rc < 0 ? rc : QIO_B200_OK;
-        }
+        const int rc = rotate_axis_tma(U, in, out, n, kdim, ldu, rows, ld_in, ld_out, MODE == MODE_LEAD_KEEP, 1, 0, 0, st);
+        if (rc != 0) return rc < 0 ? rc : QIO_B200_OK;
     }
     // N tile = 16*NT8 columns: fewest padded columns, ties to the wider tile
     int best = 1;
@@ -274,6 +269,25 @@ extern "C" int qio_b200_rotate_axis(const double *U, const double *in, double *o
     if (rows == 0) return QIO_B200_OK;
     QIO_REQUIRE(U && in && out && in != out, "rotate_axis: bad pointers");
     return dispatch_rotate_axis<MODE_CYCLIC>(U, in, out, n, n, n, rows, ld_in, n, as_stream(stream));
+}
+
+extern "C" int qio_b200_rotate_axis_batched(const double *U, const double *in, double *out, int n, long long rows,
+                                            long long ld_in, int batch, long long batch_stride_in, long long batch_stride_out,
+                                            void *stream) {
+    using namespace qio;
+    QIO_REQUIRE(n > 0 && rows >= 0 && ld_in >= rows && batch >= 0, "rotate_axis_batched: bad sizes");
+    if (rows == 0 || batch == 0) return QIO_B200_OK;
+    QIO_REQUIRE(U && in && out && in != out, "rotate_axis_batched: bad pointers");
+    QIO_REQUIRE(batch == 1 || (batch_stride_in >= ld_in * (long long)(n - 1) + rows && batch_stride_out >= rows * (long long)n),
+                "rotate_axis_batched: batch strides overlap");
+    const int rc = rotate_axis_tma(U, in, out, n, n, n, rows, ld_in, n, false, batch, batch_stride_in, batch_stride_out, as_stream(stream));
+    if (rc != 0) return rc < 0 ? rc : QIO_B200_OK;
+    for (int b = 0; b < batch; ++b) {       // shapes the TMA kernel does not take: one launch per problem
+        const int r = dispatch_rotate_axis<MODE_CYCLIC>(U, in + (long long)b * batch_stride_in, out + (long long)b * batch_stride_out,
+                                                        n, n, n, rows, ld_in, n, as_stream(stream));
+        if (r != QIO_B200_OK) return r;
+    }
+    return QIO_B200_OK;
 }
 
 extern "C" int qio_b200_contract_axis(const double *U, const double *in, double *out, int n, long long rows,

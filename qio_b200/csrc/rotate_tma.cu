@@ -17,7 +17,11 @@
 //   * B (the rotation matrix, <= 104 columns per CTA) is resident in shared memory for the whole kernel, k-major with a
 //     pitch = 2 mod 16 doubles (conflict-free for the same k-groups);
 //   * the N tiles are split 7 + 6 between the two warp columns (warps w and w + 4 share a scheduler), so that n = 100 is
-//     padded to 104 columns instead of 112.
+//     padded to 104 columns instead of 112; when K = 4 mod 8 (n = 100, 28, ...) the last slab runs ONE k-group over its four
+//     valid rows instead of two half-empty ones (K is not padded to 104 either);
+//   * batched: `batch` independent problems of the same shape (the slabs of a leading-index shard, qio_b200_rotate_axis_batched)
+//     are one launch -- the tensor map has the batch as its fourth dimension and the persistent tile loop runs over
+//     (batch, M tile).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -56,10 +60,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned long long *bar) {
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, unsigned long long *bar) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -73,7 +77,8 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 template <bool LEAD_KEEP>
 __global__ void __launch_bounds__(RT_THREADS, 1)
     rotate_tma_kernel(const __grid_constant__ CUtensorMap tmA, const double *__restrict__ U, double *__restrict__ out, int n,
-                      int kdim, long long ldu, long long rows, long long ld_out, int cols_per_cta, int np, int kpad, int stages) {
+                      int kdim, long long ldu, long long rows, long long ld_out, int cols_per_cta, int np, int kpad, int stages,
+                      int batch, long long bs_out) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double *sA = reinterpret_cast<double *>(smem_raw);
     double *sB = sA + (size_t)stages * RT_STAGE_DOUBLES;
@@ -83,7 +88,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n0 = blockIdx.y * cols_per_cta, ncols = min(cols_per_cta, n - n0);
     const int nslabs = kpad / RT_KS;
-    const long long mtiles = (rows + RT_BM - 1) / RT_BM;
+    const long long mtiles_b = (rows + RT_BM - 1) / RT_BM, mtiles = mtiles_b * batch;
+    const bool half_last = (kdim & 7) == 4;     // the last slab holds four valid k-rows: one k-group instead of two
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -108,7 +114,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
                     const int s = (int)(q % stages);
                     if (q >= stages) mbar_wait(empty + s, (unsigned)(((q / stages) - 1) & 1));
                     mbar_expect_tx(full + s, RT_STAGE_DOUBLES * sizeof(double));
-                    tma_load_3d(sA + (size_t)s * RT_STAGE_DOUBLES, &tmA, 0, ks * RT_KS, (int)(tile * (RT_BM / 16)), full + s);
+                    const long long b = tile / mtiles_b, mt = tile - b * mtiles_b;
+                    tma_load_4d(sA + (size_t)s * RT_STAGE_DOUBLES, &tmA, 0, ks * RT_KS, (int)(mt * (RT_BM / 16)), (int)b, full + s);
                 }
         }
         return;
@@ -140,9 +147,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
             mbar_wait(full + s, (unsigned)((q / stages) & 1));
             const double *a = sA + (size_t)s * RT_STAGE_DOUBLES;
             const double *b = sB + (size_t)(ks * RT_KS) * np + wn + g;
+            const bool half = half_last && ks == nslabs - 1;
 #pragma unroll
             for (int grp = 0; grp < 2; ++grp) {
-                const int r = 2 * t + grp;          // k-group: rows {0, 2, 4, 6} (+1) of the slab
+                if (half && grp == 1) break;
+                const int r = half ? t : 2 * t + grp;   // k-group: rows {0, 2, 4, 6} (+1) of the slab; {0, 1, 2, 3} of a half slab
                 double af[4], bf[RT_MAX_NT];
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi)
@@ -159,7 +168,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
             if (lane == 0) mbar_arrive(empty + s);
         }
         // epilogue: C fragment (row g, cols 2t, 2t+1) of each 8x8 tile
-        const long long m0 = tile * RT_BM;
+        const long long bidx = tile / mtiles_b, m0 = (tile - bidx * mtiles_b) * RT_BM;
+        double *outb = out + bidx * bs_out;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
             const long long m = m0 + wm + 8 * mi + g;
@@ -169,10 +179,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
                 if (ni >= nt) continue;
                 const int col = n0 + wn + 8 * ni + 2 * t;
                 if (LEAD_KEEP) {
-                    if (col < n0 + ncols) out[(long long)col * ld_out + m] = acc[mi][ni][0];
-                    if (col + 1 < n0 + ncols) out[(long long)(col + 1) * ld_out + m] = acc[mi][ni][1];
+                    if (col < n0 + ncols) outb[(long long)col * ld_out + m] = acc[mi][ni][0];
+                    if (col + 1 < n0 + ncols) outb[(long long)(col + 1) * ld_out + m] = acc[mi][ni][1];
                 } else {
-                    double *orow = out + m * ld_out;
+                    double *orow = outb + m * ld_out;
                     if (col + 1 < n0 + ncols) {
                         *reinterpret_cast<double2 *>(orow + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
                     } else if (col < n0 + ncols) {
@@ -188,28 +198,28 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static EncodeTiledFn lookup_encode_tiled() {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<EncodeTiledFn>(p);
+    return nullptr;
+}
 static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
+    static const EncodeTiledFn fn = lookup_encode_tiled();      // driver entry point: thread-safe one-time lookup
     return fn;
 }
 
 // Returns 1 if the TMA kernel took the job, 0 if the shape is not eligible (the caller falls back to rotate.cu), < 0 on error.
 int rotate_axis_tma(const double *U, const double *in, double *out, int n, int kdim, long long ldu, long long rows,
-                    long long ld_in, long long ld_out, bool lead_keep, cudaStream_t st) {
+                    long long ld_in, long long ld_out, bool lead_keep, int batch, long long bs_in, long long bs_out, cudaStream_t st) {
     if (rows % 16 != 0 || ld_in % 2 != 0 || ((uintptr_t)in % 16) != 0 || rows / 16 > 0x7fffffffLL || kdim < 1) return 0;
+    if (batch < 1 || (batch > 1 && (bs_in % 2 != 0 || bs_out % 2 != 0))) return 0;
     if (!lead_keep && (ld_out % 2 != 0 || ((uintptr_t)out % 16) != 0 || n % 2 != 0)) return 0;
     EncodeTiledFn encode = encode_tiled_fn();
     if (!encode) return 0;
-    const int kpad = (kdim + RT_KS - 1) / RT_KS * RT_KS;
+    const int kpad = (kdim + RT_KS - 1) / RT_KS * RT_KS;      // rows of B in shared memory (the TMA unit zero-fills A beyond kdim)
     const int ny = (n + RT_MAX_COLS - 1) / RT_MAX_COLS;
     const int cols_per_cta = ((n + ny - 1) / ny + 7) / 8 * 8;      // balanced column blocks, multiples of 8
     int np = cols_per_cta;
@@ -224,23 +234,24 @@ int rotate_axis_tma(const double *U, const double *in, double *out, int n, int k
     const size_t smem = (size_t)stages * RT_STAGE_DOUBLES * sizeof(double) + fixed - 1024;
 
     CUtensorMap tm;
-    const cuuint64_t gdim[3] = {16, (cuuint64_t)kdim, (cuuint64_t)(rows / 16)};
-    const cuuint64_t gstride[2] = {(cuuint64_t)ld_in * sizeof(double), 16 * sizeof(double)};
-    const cuuint32_t box[3] = {16, RT_KS, RT_BM / 16};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(in), gdim, gstride, box, estr,
+    const cuuint64_t gdim[4] = {16, (cuuint64_t)kdim, (cuuint64_t)(rows / 16), (cuuint64_t)batch};
+    const cuuint64_t gstride[3] = {(cuuint64_t)ld_in * sizeof(double), 16 * sizeof(double),
+                                   (cuuint64_t)(batch > 1 ? bs_in : ld_in * (long long)kdim) * sizeof(double)};
+    const cuuint32_t box[4] = {16, RT_KS, RT_BM / 16, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double *>(in), gdim, gstride, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return 0;
-    const long long mtiles = (rows + RT_BM - 1) / RT_BM;
+    const long long mtiles = (rows + RT_BM - 1) / RT_BM * batch;
     const int gx = (int)std::min<long long>(mtiles, std::max(1, sm_count() / ny));
     dim3 grid(gx, ny);
     if (lead_keep) {
         QIO_CUDA(cudaFuncSetAttribute(rotate_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rotate_tma_kernel<true><<<grid, RT_THREADS, smem, st>>>(tm, U, out, n, kdim, ldu, rows, ld_out, cols_per_cta, np, kpad, stages);
+        rotate_tma_kernel<true><<<grid, RT_THREADS, smem, st>>>(tm, U, out, n, kdim, ldu, rows, ld_out, cols_per_cta, np, kpad, stages, batch, bs_out);
     } else {
         QIO_CUDA(cudaFuncSetAttribute(rotate_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rotate_tma_kernel<false><<<grid, RT_THREADS, smem, st>>>(tm, U, out, n, kdim, ldu, rows, ld_out, cols_per_cta, np, kpad, stages);
+        rotate_tma_kernel<false><<<grid, RT_THREADS, smem, st>>>(tm, U, out, n, kdim, ldu, rows, ld_out, cols_per_cta, np, kpad, stages, batch, bs_out);
     }
     QIO_LAUNCH_CHECK();
     return 1;

@@ -29,10 +29,9 @@
 
 #include <type_traits>
 
-#include <stdlib.h>
-
 #define QIO_LS_TIMED 1      // this kernel reports the line-search stage timers in its summary
 #include "linesearch.cuh"
+#include "ll.cuh"
 #include "sweep3.cuh"
 
 namespace qio {
@@ -57,7 +56,8 @@ struct SweepParams {
     unsigned *bar;             // [0] arrival counter (monotone), [1] generation
     double *summary;           // [32]
     int rank, nranks;
-    unsigned long long epoch;  // distinguishes launches in the mailbox tags
+    unsigned epoch;            // launch epoch of the mailbox tags (ll.cuh: mailbox_tag)
+    double *blocks_out;        // (P, 24) or NULL: the block each search ran on (decision audit)
     double *const *mailboxes;  // [nranks] peer-mapped mailbox bases, layout [2][nranks][MB_STRIDE]; NULL if nranks == 1
 };
 
@@ -579,27 +579,26 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepParams p) {
             sb[tid] = __ldcg(src + (size_t)nsb * SB_DOUBLES + tid);
         }
         if (p.nranks > 1) {
-            // Every 16-byte word carries (value, tag): one NVLink store per element, no fence, no separate flag --
-            // the receiver spins on the tag of each word it needs (the "LL" idea).  Slots alternate with the step
-            // parity; a slot is rewritten two steps later, after every reader has moved on.
+            // Every 16-byte word carries the value and, in both 8-byte halves, the tag (ll.cuh): one NVLink store per
+            // element, no fence, no separate flag -- the receiver spins on the word it needs.  Slots alternate with the
+            // step parity; a slot is rewritten two steps later, after every reader has moved on.
             const int par = t & 1;
-            const unsigned long long tag = (p.epoch << 32) | (unsigned long long)(t + 1);
+            const unsigned tag = mailbox_tag(p.epoch, t);
             ls_sync<SEARCH_THREADS>();
             if (tid < 256) {
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(sb[tid]);
                 for (int dst = 0; dst < p.nranks; ++dst) {
                     unsigned long long *w = reinterpret_cast<unsigned long long *>(
                         p.mailboxes[dst] + ((size_t)par * p.nranks + p.rank) * MB_STRIDE) + 2 * tid;
-                    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(w), "l"(bits), "l"(tag) : "memory");
+                    ll_store(w, bits, tag);
                 }
                 double acc = 0.0;
                 for (int r = 0; r < p.nranks; ++r) {
                     const unsigned long long *w = reinterpret_cast<const unsigned long long *>(
                         p.mailboxes[p.rank] + ((size_t)par * p.nranks + r) * MB_STRIDE) + 2 * tid;
-                    unsigned long long v, g;
-                    do {
-                        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(g) : "l"(w) : "memory");
-                    } while (g != tag);
+                    unsigned long long v;
+                    while (!ll_load(w, v, tag)) {
+                    }
                     acc += __longlong_as_double((long long)v);
                 }
                 sb[tid] = acc;
@@ -620,6 +619,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepParams p) {
         const bool i_in = p.inactive[i] != 0, j_in = p.inactive[j] != 0;       // L2 latency overlaps the contraction
         ls_sync<SEARCH_THREADS>();
         block_from_superblock(sb, Tmat, sbtmp, blk, pc);
+        if (p.blocks_out && tid < QIO_B200_BLOCK_DOUBLES) p.blocks_out[(size_t)t * QIO_B200_BLOCK_DOUBLES + tid] = blk[tid];
         if (tid == 0) {
             const long long c1 = clock64();
             ls.prof[6] += c1 - c0;
@@ -838,13 +838,9 @@ static size_t sweep_ws_bytes(int n) {
 
 }  // namespace qio
 
-// 3 = pipelined kernel without grid barriers (sweep3.cu), 2 = barrier kernel of this file.  QIO_B200_SWEEP_ENGINE=2|3
-// forces one (3 only where it fits); the default is 3 wherever the owned W columns fit in shared memory.
-static int sweep_engine(int n, int na) {
-    const char *e = getenv("QIO_B200_SWEEP_ENGINE");
-    if (e && e[0] == '2') return 2;
-    return qio::sweep3_supported(n, na) ? 3 : 2;
-}
+// 3 = pipelined kernel without grid barriers (sweep3.cu) wherever the owned W columns fit in shared memory,
+// 2 = barrier kernel of this file.  A caller forces one through qio_b200_sweep_options.engine.
+static int sweep_engine(int n, int na) { return qio::sweep3_supported(n, na) ? 3 : 2; }
 
 extern "C" int qio_b200_sweep_engine(int n, int na) { return sweep_engine(n, na); }
 
@@ -870,7 +866,8 @@ extern "C" int qio_b200_sweep_reset(double *W, int n, void *stream) {
 extern "C" int qio_b200_sweep_cycle(double *gamma, double *S, double *U, double *W, int n, int a0, int na,
                                     const int32_t *pairs, int P, const int32_t *inactive,
                                     const qio_b200_theta_tables *h_tables, qio_b200_ls_result *results,
-                                    double *summary, void *workspace, const qio_b200_peers *h_peers, void *stream) {
+                                    double *summary, void *workspace, const qio_b200_peers *h_peers,
+                                    const qio_b200_sweep_options *h_opts, void *stream) {
     using namespace qio;
     QIO_REQUIRE(n >= 2 && P >= 0, "sweep_cycle: bad sizes");
     QIO_REQUIRE(a0 >= 0 && na >= 0 && a0 + na <= n, "sweep_cycle: bad shard range");
@@ -883,8 +880,18 @@ extern "C" int qio_b200_sweep_cycle(double *gamma, double *S, double *U, double 
     QIO_REQUIRE(nranks == 1 || (h_peers->mailboxes && h_peers->rank >= 0 && h_peers->rank < nranks), "sweep_cycle: bad peers");
     QIO_REQUIRE(nranks > 1 || (a0 == 0 && na == n), "sweep_cycle: a partial shard needs peers");
     cudaStream_t st = as_stream(stream);
-    if (sweep_engine(n, na) == 3)
-        return sweep3_launch(gamma, S, U, W, n, a0, na, pairs, P, inactive, h_tables, results, summary, workspace, h_peers, st);
+    qio_b200_sweep_options opts;
+    memset(&opts, 0, sizeof(opts));
+    if (h_opts) opts = *h_opts;
+    QIO_REQUIRE(opts.engine == 0 || opts.engine == 2 || opts.engine == 3, "sweep_cycle: options.engine must be 0, 2 or 3");
+    QIO_REQUIRE(nranks == 1 || (h_peers->epoch >= 1 && h_peers->epoch < (1u << (32 - LL_STEP_BITS))), "sweep_cycle: mailbox epoch must be in 1..4095");
+    const int engine = opts.engine ? opts.engine : sweep_engine(n, na);
+    if (engine == 3) {
+        if (opts.timers)
+            return sweep3_timed_launch(gamma, S, U, W, n, a0, na, pairs, P, inactive, h_tables, results, summary, workspace, h_peers, opts, st);
+        return sweep3_launch(gamma, S, U, W, n, a0, na, pairs, P, inactive, h_tables, results, summary, workspace, h_peers, opts, st);
+    }
+    QIO_REQUIRE((long long)P + 1 < (1LL << LL_STEP_BITS), "sweep_cycle: too many pairs for the tag width");
     char *ws = reinterpret_cast<char *>(workspace);
     QIO_CUDA(cudaMemsetAsync(ws, 0, WS_HEADER, st));
     QIO_CUDA(cudaMemsetAsync(summary, 0, 32 * sizeof(double), st));
@@ -909,7 +916,8 @@ extern "C" int qio_b200_sweep_cycle(double *gamma, double *S, double *U, double 
     p.summary = summary;
     p.rank = h_peers ? h_peers->rank : 0;
     p.nranks = nranks;
-    p.epoch = h_peers ? (unsigned long long)h_peers->epoch : 0ull;
+    p.epoch = h_peers ? h_peers->epoch : 0u;
+    p.blocks_out = opts.blocks_out;
     p.mailboxes = nranks > 1 ? reinterpret_cast<double *const *>(h_peers->mailboxes) : nullptr;
     int blocks_per_sm = 0;
     QIO_REQUIRE(n <= 4096, "sweep_cycle: n too large for the shared-memory W rows");
@@ -957,6 +965,13 @@ extern "C" int qio_b200_ipc_alloc(size_t bytes, void **ptr, unsigned char *handl
     QIO_CUDA(cudaIpcGetMemHandle(&h, *ptr));
     static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
     memcpy(handle64, &h, 64);
+    return QIO_B200_OK;
+}
+
+extern "C" int qio_b200_ipc_clear(void *ptr, size_t bytes, void *stream) {
+    using namespace qio;
+    QIO_REQUIRE(ptr && bytes > 0, "ipc_clear: bad arguments");
+    QIO_CUDA(cudaMemsetAsync(ptr, 0, bytes, as_stream(stream)));
     return QIO_B200_OK;
 }
 

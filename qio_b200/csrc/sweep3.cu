@@ -21,19 +21,22 @@
 //    needs cached in shared memory and rotated locally) -> post the partial -> stream the rest of rotation w.
 //  * Dormant orbitals: rows of orbitals that have not yet appeared in any super block are skipped by the update and caught
 //    up with the accumulated rotation when they wake (see catch_up).
-//  * Signalling is one-directional and tagged: angle records, partials and totals are 16-byte (value, tag) words written
-//    with a single store and polled by the consumer ("LL" style).  Slot counts follow from how far the parties can drift
-//    apart (see the constants).  Every wait has a time-out that aborts the whole kernel (summary[3]).
+//  * Signalling is one-directional and tagged: angle records, partials and totals are 16-byte words written with a single
+//    store and polled by the consumer; each 8-byte half carries 32 data bits and the tag, so a torn observation is
+//    rejected (ll.cuh).  Slot counts follow from how far the parties can drift apart (see the constants).  Every wait has
+//    a time-out that aborts the whole kernel (summary[3]); until the first super block has arrived a longer one applies
+//    (launch skew between ranks).  All signalling words of the workspace are cleared by the launch; only the peer
+//    mailboxes survive a launch and carry the caller's epoch in their tags.
 //
 // The launch is cooperative only to guarantee that all CTAs are co-resident.  n > 1024, or shapes where a worker would own
 // more than four row pieces, stay on the barrier kernel of sweep2.cu (see qio_b200_sweep_cycle).
-#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <type_traits>
 
 #include "linesearch.cuh"
+#include "ll.cuh"
 #include "sweep3.cuh"
 
 // The file is compiled twice: as is (no phase timers: the default kernel) and through sweep3_timed.cu with QIO_S3_TIMED
@@ -70,7 +73,6 @@ constexpr int MAXN3 = 1024;      // largest n of the pipelined kernel (rank / ac
 constexpr int CU_COLS = 32;       // columns per catch-up chunk (one per lane)
 constexpr int CU_PITCH = 36;      // pitch of the staged catch-up vectors (conflict-free B fragments)
 constexpr int NRED = 4;          // reducer CTAs (each sums a quarter of the entries)
-constexpr unsigned long long TIMEOUT_NS = 4000000000ull;
 constexpr int AUX_CTA = NRED + 1;
 constexpr int FIRST_WORKER = NRED + 2;
 
@@ -83,13 +85,14 @@ struct Params {
     ThetaTablesDev tab;
     qio_b200_ls_result *results;
     double *summary;
-    unsigned long long *ring;   // [RING][4]: (cos bits, tag), (sin bits, tag); tag = 2 (k + 1) + accepted
-    unsigned *abort_flag;
-    unsigned long long *pbuf;   // [SLOTS][nworkers][SB_MAX][2] tagged partial entries (value bits, (launch << 32) | (k + 1))
-    unsigned long long launch_id;
-    unsigned long long *tot;    // [SLOTS][TOT_WORDS][2] (value bits, tag = k + 1)
+    unsigned long long *ring;   // [RING][4]: tagged words of cos and sin; tag = 2 (k + 1) + accepted
+    unsigned *abort_flag;       // [0] != 0: some wait timed out, everybody leaves; [1] != 0: the first super block has arrived
+    unsigned long long *pbuf;   // [SLOTS][nworkers][SB_MAX][2] tagged partial entries, tag = k + 1 (cleared by the launch)
+    unsigned long long *tot;    // [SLOTS][TOT_WORDS][2] tagged totals, tag = k + 1
+    unsigned long long timeout_ns, startup_timeout_ns;
+    double *blocks_out;         // (P, 24) or NULL: the block each search ran on (decision audit)
     int rank, nranks;
-    unsigned long long epoch;
+    unsigned epoch;             // launch epoch of the mailbox tags (ll.cuh: mailbox_tag)
     double *const *mailboxes;   // [nranks] bases, layout [MB_SLOTS][nranks][SB_MAX][2]
     const int32_t *dtab;        // [P][DT_STRIDE] per-pair table (see build_dtab_kernel)
     int nworkers;               // workers that own at least one column
@@ -113,12 +116,6 @@ __device__ __forceinline__ unsigned long long gtimer() {     // phase timers: on
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 #endif
-}
-__device__ __forceinline__ void ll_store(unsigned long long *w, unsigned long long bits, unsigned long long tag) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(w), "l"(bits), "l"(tag) : "memory");
-}
-__device__ __forceinline__ void ll_load(const unsigned long long *w, unsigned long long &bits, unsigned long long &tag) {
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tag) : "l"(w) : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     unsigned v;
@@ -165,7 +162,7 @@ __device__ __forceinline__ bool spin_until(const Params &p, Pred pred) {
         if (pred()) return true;
         if ((++it & 0xff) == 0) {
             if (ld_volatile_u32(p.abort_flag) != 0) return false;
-            if (wtimer() - t0 > TIMEOUT_NS) {
+            if (wtimer() - t0 > (ld_volatile_u32(p.abort_flag + 1) != 0 ? p.timeout_ns : p.startup_timeout_ns)) {
                 atomicExch(p.abort_flag, 1u);
                 return false;
             }
@@ -226,14 +223,15 @@ __global__ void build_dtab_kernel(const int32_t *__restrict__ pairs, const int32
 // Angle record k.  Returns false on abort.
 __device__ __forceinline__ bool read_record(const Params &p, int k, int &accepted, double &c, double &s) {
     const unsigned long long *w = p.ring + (size_t)(k & (RING - 1)) * 4;
-    unsigned long long cb = 0, sbits = 0, t0 = 0, t1 = 0;
-    const unsigned long long want = 2ull * (unsigned long long)(k + 1);
+    unsigned long long cb = 0, sbits = 0;
+    unsigned t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    const unsigned want = (unsigned)(k + 1);
     const bool ok = spin_until(p, [&]() {
-        ll_load(w, cb, t0);
-        ll_load(w + 2, sbits, t1);
-        return (t0 >> 1) == (want >> 1) && t0 == t1;
+        ll_load_tags(w, cb, t0, t1);
+        ll_load_tags(w + 2, sbits, t2, t3);
+        return (t0 >> 1) == want && t0 == t1 && t0 == t2 && t0 == t3;
     });
-    accepted = (int)(t0 & 1ull);
+    accepted = (int)(t0 & 1u);
     c = __longlong_as_double((long long)cb);
     s = __longlong_as_double((long long)sbits);
     return ok;
@@ -539,7 +537,7 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
     // orbits of the rotation inside E x E: X = {IJ} + F (rotated) or X = E (not rotated); an orbit has 1, 2 or 4 rows
     const int nx = rot ? e - 1 : e;              // size of X
     const int m3 = m * m * m, ndot = sm.npieces * m3;
-    const unsigned long long ptag = (p.launch_id << 32) | (unsigned long long)(st.slot + 1);
+    const unsigned ptag = (unsigned)(st.slot + 1);
     unsigned long long *pslot = p.pbuf + ((size_t)(st.slot & (SLOTS - 1)) * p.nworkers + widx) * SB_MAX * 2;
     auto tile_pass = [&](int t0, int tl) {
         const int tv = tl / V, nitems = nx * nx * tv;
@@ -921,7 +919,7 @@ __device__ __forceinline__ void reducer_main(const Params &p, double *scratch /*
         // `ns` sub-sums per entry over interleaved subsets of the workers: every thread has 8 tagged loads in flight and
         // re-polls a batch until all its tags are those of super block k
         const int ns = nl > 0 ? max(1, min(8, THREADS / nl)) : 1;
-        const unsigned long long want = (p.launch_id << 32) | (unsigned long long)(k + 1);
+        const unsigned want = (unsigned)(k + 1);
         const unsigned long long *pb = p.pbuf + (size_t)slot * p.nworkers * SB_MAX * 2;
         bool ok = true;
         for (int it = tid; it < nl * ns; it += THREADS) {
@@ -930,17 +928,15 @@ __device__ __forceinline__ void reducer_main(const Params &p, double *scratch /*
 #pragma unroll
             for (int u = 0; u < 8; ++u) a8[u] = 0.0;
             for (int w0 = sub; w0 < p.nworkers; w0 += 8 * ns) {
-                unsigned long long v[8], g[8];
+                unsigned long long v[8];
                 ok &= spin_until(p, [&]() {
                     bool all = true;
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int wk = w0 + u * ns;
-                        if (wk < p.nworkers) ll_load(pb + ((size_t)wk * SB_MAX + e_lo + el) * 2, v[u], g[u]);
-                        else { v[u] = 0ull; g[u] = want; }
+                        if (wk < p.nworkers) all &= ll_load(pb + ((size_t)wk * SB_MAX + e_lo + el) * 2, v[u], want);
+                        else v[u] = 0ull;
                     }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) all &= (g[u] == want);
                     return all;
                 });
 #pragma unroll
@@ -966,14 +962,14 @@ __device__ __forceinline__ void reducer_main(const Params &p, double *scratch /*
             const int e = e_lo + el;
             const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
             if (p.nranks > 1) {
-                const unsigned long long tag = (p.epoch << 32) | (unsigned long long)(k + 1);
+                const unsigned tag = mailbox_tag(p.epoch, k);
                 for (int dst = 0; dst < p.nranks; ++dst) {
                     unsigned long long *w = reinterpret_cast<unsigned long long *>(p.mailboxes[dst]) +
                                             (((size_t)(k & (MB_SLOTS - 1)) * p.nranks + p.rank) * SB_MAX + e) * 2;
                     ll_store(w, bits, tag);
                 }
             } else {
-                ll_store(p.tot + ((size_t)slot * TOT_WORDS + e) * 2, bits, (unsigned long long)(k + 1));
+                ll_store(p.tot + ((size_t)slot * TOT_WORDS + e) * 2, bits, (unsigned)(k + 1));
             }
         }
         __syncthreads();
@@ -1004,7 +1000,7 @@ __device__ __forceinline__ void aux_main(const Params &p, int *flag_sm, double *
             const int spin = tid / (m * m), r = tid - spin * m * m, pp = r / m, qq = r - pp * m;
             const double v = __ldcg(p.gamma + (2 * (size_t)flag_sm[2 + pp] + spin) * ld + 2 * flag_sm[2 + qq] + spin);
             ll_store(p.tot + ((size_t)(k & (SLOTS - 1)) * TOT_WORDS + SB_MAX + tid) * 2,
-                     (unsigned long long)__double_as_longlong(v), (unsigned long long)(k + 1));
+                     (unsigned long long)__double_as_longlong(v), (unsigned)(k + 1));
         }
         __syncthreads();
     };
@@ -1095,29 +1091,33 @@ __device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
             const int word = is_g ? SB_MAX + (e - ne) : e;
             double acc = 0.0;
             if (p.nranks > 1 && !is_g) {
-                const unsigned long long tag = (p.epoch << 32) | (unsigned long long)(k + 1);
-                for (int r = 0; r < p.nranks; ++r) {
-                    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(p.mailboxes[p.rank]) +
-                                                  (((size_t)(k & (MB_SLOTS - 1)) * p.nranks + r) * SB_MAX + e) * 2;
-                    unsigned long long v = 0, g = 0;
+                // the ranks' totals, eight loads in flight, added in rank order (identical on every rank)
+                const unsigned tag = mailbox_tag(p.epoch, k);
+                const unsigned long long *w0 = reinterpret_cast<const unsigned long long *>(p.mailboxes[p.rank]) +
+                                               ((size_t)(k & (MB_SLOTS - 1)) * p.nranks * SB_MAX + e) * 2;
+                for (int r0 = 0; r0 < p.nranks; r0 += 8) {
+                    unsigned long long v[8];
                     ok &= spin_until(p, [&]() {
-                        ll_load(w, v, g);
-                        return g == tag;
+                        bool all = true;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (r0 + u < p.nranks) all &= ll_load(w0 + (size_t)(r0 + u) * SB_MAX * 2, v[u], tag);
+                        return all;
                     });
-                    acc += __longlong_as_double((long long)v);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (r0 + u < p.nranks) acc += __longlong_as_double((long long)v[u]);
                 }
             } else {
                 const unsigned long long *w = p.tot + ((size_t)(k & (SLOTS - 1)) * TOT_WORDS + word) * 2;
-                unsigned long long v = 0, g = 0;
-                ok &= spin_until(p, [&]() {
-                    ll_load(w, v, g);
-                    return g == (unsigned long long)(k + 1);
-                });
+                unsigned long long v = 0;
+                ok &= spin_until(p, [&]() { return ll_load(w, v, (unsigned)(k + 1)); });
                 acc = __longlong_as_double((long long)v);
             }
             sm.sb[b][word] = acc;
         }
         if (!ok) sm.fetch_abort = 1;
+        if (k == 0 && ft == 0 && ok) atomicExch(p.abort_flag + 1, 1u);      // start-up is over: the normal time-out applies
         named_sync<6, FETCH_THREADS>();
         if (ft == 0) sm.sb_ok[b] = sm.fetch_abort ? 0 : 1;
         __threadfence_block();
@@ -1225,6 +1225,8 @@ __device__ __forceinline__ void search_main(const Params &p, SearchSmem &sm) {
                 make_coef(sm.blk, sm.pc);
                 sm.ls.flags = 0;
             }
+            if (p.blocks_out && tid >= 32 && tid < 32 + QIO_B200_BLOCK_DOUBLES)
+                p.blocks_out[(size_t)k * QIO_B200_BLOCK_DOUBLES + (tid - 32)] = sm.blk[tid - 32];
             ls_sync<SEARCH_THREADS>();
         }
         named_arrive_id<THREADS>(4 + b);                    // empty[b]: the prefetch warps may overwrite sm.sb[b]
@@ -1237,7 +1239,7 @@ __device__ __forceinline__ void search_main(const Params &p, SearchSmem &sm) {
         // the angle record is published by thread 0 the moment the scan has decided (before the margins are taken)
         auto publish = [&](bool accepted, double cth, double sth) {
             unsigned long long *w = p.ring + (size_t)(k & (RING - 1)) * 4;
-            const unsigned long long tag = 2ull * (unsigned long long)(k + 1) + (accepted ? 1ull : 0ull);
+            const unsigned tag = 2u * (unsigned)(k + 1) + (accepted ? 1u : 0u);
             ll_store(w, (unsigned long long)__double_as_longlong(cth), tag);
             ll_store(w + 2, (unsigned long long)__double_as_longlong(sth), tag);
         };
@@ -1356,20 +1358,23 @@ bool sweep3_supported(int n, int na) {
 
 int S3_LAUNCH(double *gamma, double *S, double *U, double *W, int n, int a0, int na, const int32_t *pairs, int P,
                   const int32_t *inactive, const qio_b200_theta_tables *h_tables, qio_b200_ls_result *results,
-                  double *summary, void *workspace, const qio_b200_peers *h_peers, cudaStream_t st) {
+                  double *summary, void *workspace, const qio_b200_peers *h_peers, const qio_b200_sweep_options &opts,
+                  cudaStream_t st) {
     using namespace S3_NS;
-#ifndef QIO_S3_TIMED
-    if (getenv("QIO_B200_SWEEP_TIMERS"))
-        return sweep3_timed_launch(gamma, S, U, W, n, a0, na, pairs, P, inactive, h_tables, results, summary, workspace, h_peers, st);
-#endif
     const int grid = sm_count();
     Params p;
     const size_t wsm = worker_smem_bytes(n, na, grid, p.nworkers, p.granule, p.wc_cols);
-    QIO_REQUIRE(wsm > 0 && wsm <= 200 * 1024, "sweep_cycle: problem does not fit the pipelined kernel");
+    if (!(wsm > 0 && wsm <= 200 * 1024)) {
+        set_error("sweep_cycle: problem does not fit the pipelined kernel");
+        return QIO_B200_ERR_UNSUPPORTED;
+    }
     const Layout L = ws_layout(grid, n);
     QIO_REQUIRE((long long)P <= (long long)n * (n - 1) / 2 + 1, "sweep_cycle: more pairs than n (n - 1) / 2 (pipelined kernel)");
+    QIO_REQUIRE((long long)P + 1 < (1LL << LL_STEP_BITS), "sweep_cycle: too many pairs for the tag width");
     char *ws = reinterpret_cast<char *>(workspace);
-    QIO_CUDA(cudaMemsetAsync(ws, 0, L.off_pbuf, st));
+    // every signalling word of the workspace (angle ring, abort / started flags, totals, partials) starts at zero: tags
+    // are step indices + 1 and need no launch counter (the library keeps no state between calls)
+    QIO_CUDA(cudaMemsetAsync(ws, 0, L.off_dtab, st));
     QIO_CUDA(cudaMemsetAsync(summary, 0, 32 * sizeof(double), st));
     p.S = S;
     p.gamma = gamma;
@@ -1388,15 +1393,17 @@ int S3_LAUNCH(double *gamma, double *S, double *U, double *W, int n, int a0, int
     p.abort_flag = reinterpret_cast<unsigned *>(ws + L.off_abort);
     p.tot = reinterpret_cast<unsigned long long *>(ws + L.off_tot);
     p.pbuf = reinterpret_cast<unsigned long long *>(ws + L.off_pbuf);
-    static unsigned long long launch_counter = 0;
-    p.launch_id = ++launch_counter;
+    p.timeout_ns = 1000000ull * (opts.timeout_ms ? opts.timeout_ms : 4000u);
+    p.startup_timeout_ns = 1000000ull * (opts.startup_timeout_ms ? opts.startup_timeout_ms : 60000u);
+    p.blocks_out = opts.blocks_out;
     p.dtab = reinterpret_cast<const int32_t *>(ws + L.off_dtab);
     p.wg = reinterpret_cast<double *>(ws + L.off_wg);
     p.rg = reinterpret_cast<double *>(ws + L.off_rg);
     QIO_REQUIRE(L.off_wg + sizeof(double) * (size_t)p.nworkers * n * p.wc_cols <= L.off_rg, "sweep_cycle: workspace too small for the private W columns");
     p.rank = h_peers ? h_peers->rank : 0;
     p.nranks = h_peers ? h_peers->nranks : 1;
-    p.epoch = h_peers ? (unsigned long long)h_peers->epoch : 0ull;
+    p.epoch = h_peers ? h_peers->epoch : 0u;
+    QIO_REQUIRE(p.nranks == 1 || (p.epoch >= 1 && p.epoch < (1u << (32 - LL_STEP_BITS))), "sweep_cycle: mailbox epoch must be in 1..4095");
     p.mailboxes = p.nranks > 1 ? reinterpret_cast<double *const *>(h_peers->mailboxes) : nullptr;
     size_t dyn = std::max(wsm, sizeof(SearchSmem));
     dyn = std::max(dyn, sizeof(double) * 8 * SB_MAX + 256);

@@ -1,4 +1,4 @@
-// The pipelined sweep kernel with its phase timers compiled in (see sweep3.cu); launched when QIO_B200_SWEEP_TIMERS is set.
+// The pipelined sweep kernel with its phase timers compiled in (see sweep3.cu); launched when qio_b200_sweep_options.timers is set.
 #define QIO_S3_TIMED 1
 #define QIO_LS_TIMED 1
 #define S3_NS s3t

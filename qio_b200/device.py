@@ -183,6 +183,13 @@ def rotate_axis(U, src, dst, n, rows, ld_in):
     return dst
 
 
+def rotate_axis_batched(U, src, dst, n, rows, ld_in, batch, bs_in, bs_out):
+    """``batch`` cyclic single-axis passes (see rotate_axis) in one launch."""
+    check(lib.qio_b200_rotate_axis_batched(_ptr(U), _ptr(src), _ptr(dst), n, int(rows), int(ld_in), int(batch), int(bs_in),
+                                            int(bs_out), _stream()), 'rotate_axis_batched')
+    return dst
+
+
 def jacobi_cycle(gamma, Gamma, U, n, pairs, mask, tables):
     P = int(pairs.shape[0])
     results = torch.empty(max(P, 1) * LS_DTYPE.itemsize, dtype=torch.uint8, device=require_cuda())
@@ -212,9 +219,13 @@ def sweep_reset(W, n):
     check(lib.qio_b200_sweep_reset(_ptr(W), n, _stream()), 'sweep_reset')
 
 
-def sweep_cycle(gamma, S, U, W, n, pairs, mask, tables, a0=0, na=None, peers=None):
+def sweep_cycle(gamma, S, U, W, n, pairs, mask, tables, a0=0, na=None, peers=None, engine=0, timers=False,
+                blocks_out=None, timeout_ms=0, startup_timeout_ms=0):
     """One cycle on the deferred-axis state (S, W); returns (results bytes, summary).
-    ``peers`` is a qio_b200.peers.PeerGroup (multi-GPU) or None."""
+    ``peers`` is a qio_b200.peers.PeerGroup (multi-GPU) or None.  ``engine``: 0 = automatic, 2 = barrier kernel,
+    3 = pipelined kernel; ``timers``: the build that carries phase timers; ``blocks_out``: (P, 24) device tensor that
+    receives the pair block every line search ran on (see audit_decisions).  All of it travels in the call's options
+    struct -- the library keeps no state and reads no environment variables."""
     na = n if na is None else na
     P = int(pairs.shape[0])
     results = torch.empty(max(P, 1) * LS_DTYPE.itemsize, dtype=torch.uint8, device=require_cuda())
@@ -222,11 +233,38 @@ def sweep_cycle(gamma, S, U, W, n, pairs, mask, tables, a0=0, na=None, peers=Non
     ws = torch.empty(int(lib.qio_b200_sweep_workspace_bytes(n)), dtype=torch.uint8, device=require_cuda())
     if peers is not None:
         peers.next_epoch()
+    opts = _lib.SweepOptions(int(engine), 1 if timers else 0, int(timeout_ms), int(startup_timeout_ms),
+                             0 if blocks_out is None else blocks_out.data_ptr())
     check(lib.qio_b200_sweep_cycle(_ptr(gamma), _ptr(S), _ptr(U), _ptr(W), n, a0, na, _ptr(pairs), P, _ptr(mask),
                                     ctypes.byref(tables.struct), _ptr(results), _ptr(summary), _ptr(ws),
-                                    ctypes.byref(peers.struct) if peers is not None else None, _stream()),
-          'sweep_cycle')
+                                    ctypes.byref(peers.struct) if peers is not None else None, ctypes.byref(opts),
+                                    _stream()), 'sweep_cycle')
     return results[:P * LS_DTYPE.itemsize], summary
+
+
+def audit_decisions(records: np.ndarray, blocks, pairs, mask, tables, near_tie=1e-12):
+    """Re-derives every line-search decision of a cycle from the pair blocks the sweep kernel itself searched
+    (``blocks_out`` of sweep_cycle), in the reference's own floating-point operation order (strict_order: 16-term sums,
+    library log -- qio/grad/jacobi.py:15-60,117-158), as one batched launch, and compares it with the decisions the kernel
+    took with its polynomial cost.  Returns a dict: pairs, mismatches (pair indices whose coarse / fine index differ),
+    near_ties (pairs whose smaller margin is below ``near_tie``), unexplained (mismatches that are NOT near-ties: those
+    would be a real defect), min_fine_margin, min_coarse_margin."""
+    P = int(pairs.shape[0])
+    if P == 0:
+        return dict(pairs=0, mismatches=[], near_ties=[], unexplained=[], min_fine_margin=float('inf'),
+                    min_coarse_margin=float('inf'))
+    strict = results_to_numpy(pair_linesearch(blocks, pairs, mask, tables, strict_order=True))
+    diff = (strict['coarse_index'] != records['coarse_index']) | (strict['fine_index'] != records['fine_index'])
+    # a pair neither of whose orbitals is inactive has an identically zero cost: no decision to audit
+    fm = np.where(np.isfinite(records['fine_margin']), records['fine_margin'], np.inf)
+    cm = np.where(np.isfinite(records['coarse_margin']), records['coarse_margin'], np.inf)
+    sfm = np.where(np.isfinite(strict['fine_margin']), strict['fine_margin'], np.inf)
+    scm = np.where(np.isfinite(strict['coarse_margin']), strict['coarse_margin'], np.inf)
+    margin = np.minimum(np.minimum(fm, cm), np.minimum(sfm, scm))
+    tie = margin < near_tie
+    return dict(pairs=P, mismatches=np.nonzero(diff)[0].tolist(), near_ties=np.nonzero(tie)[0].tolist(),
+                unexplained=np.nonzero(diff & ~tie)[0].tolist(), min_fine_margin=float(fm.min()),
+                min_coarse_margin=float(cm.min()))
 
 
 def sweep_engine(n, na=None):
@@ -234,7 +272,8 @@ def sweep_engine(n, na=None):
 
 
 def check_sweep_summary(summary_host):
-    """Raises if the pipelined sweep kernel reported a timed-out wait (summary[3])."""
+    """Raises if the pipelined sweep kernel reported a timed-out wait (summary[3]).  The cycle is then incomplete and
+    S, W, gamma, U are partly rotated: callers mark their state as poisoned and refuse further cycles / flushes."""
     if float(summary_host[3]) != 0.0:
         raise QioCudaError('sweep_cycle: a wait inside the pipelined kernel timed out; the cycle is incomplete')
 
@@ -270,3 +309,11 @@ def pair_entropy(blocks, supp=None):
     check(lib.qio_b200_pair_entropy(_ptr(blocks), _ptr(supp), P, _ptr(s_pair), _ptr(eig), _ptr(flags), _stream()),
           'pair_entropy')
     return s_pair, eig, flags
+
+
+def mutual_information_matrix(s1, s_pair, pairs, n):
+    """(n, n) device matrix I_ij = S_i + S_j - S_ij for ``pairs`` (P, 2); zero elsewhere (extension a-9)."""
+    I = empty(n, n)
+    check(lib.qio_b200_mutual_information(_ptr(s1), _ptr(s_pair), _ptr(pairs), int(pairs.shape[0]), n, _ptr(I), _stream()),
+          'mutual_information')
+    return I

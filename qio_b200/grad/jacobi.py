@@ -7,6 +7,11 @@ names, positional signatures and return values, executed by the CUDA library.
     minimize_orb_corr_jacobi(gamma, Gamma, inactive_indices, max_cycle)   jacobi.py:161-242
     reorder_fast / reorder_occ / reorder                             jacobi.py:244-420
 
+A cycle's warn / raise conditions of ``shannon`` (entropy.py:15-20) are OR-ed over the whole cycle on the device and
+re-created on the host after it: where the reference raises ValueError at the offending ``jacobi_cost`` call, here the
+remaining rotations of that cycle have already been applied when the exception surfaces (the RDMs are then those after
+the cycle, not those at the offending pair).
+
 RDM arguments may be numpy arrays (uploaded per call, results returned as numpy) or CUDA tensors
 (used in place, results returned as CUDA tensors).  What stays on the host, by design: numpy's legacy
 global RNG (rand, rand, shuffle -- in the reference's call order, so ``np.random.seed`` reproduces
@@ -104,50 +109,94 @@ def random_start(n):
     return expm(X)
 
 
-# Which device implementation of the cycle runs: 'deferred' = one persistent kernel on the deferred-axis
-# state (S, W) (sweep2.cu, the fast path); 'materialized' = one search + one Givens launch per pair on the
-# fully materialised 2-RDM (sweep.cu, kept as an independent cross-check).
+# Which device implementation of the cycle runs:
+#   'deferred'          one persistent kernel on the deferred-axis state (S, W): the pipelined kernel without grid
+#                       barriers (sweep3.cu) wherever it fits, else the barrier kernel (sweep2.cu) -- the fast path;
+#   'deferred-barrier'  the same state, forced onto the one-grid-barrier-per-pair kernel (sweep2.cu);
+#   'materialized'      one search + one Givens launch per pair on the fully materialised 2-RDM (sweep.cu), kept as an
+#                       independent cross-check.
 ENGINE = 'deferred'
+# Decision audit of the deferred engines: every cycle also returns the 24-number block each line search ran on, and one
+# batched launch re-derives all decisions from those blocks in the reference's own operation order (strict_order).  A
+# decision that differs although its margins are not within rounding (1e-12) raises; near-ties are logged (SURVEY.md
+# section 7, "Discrete decisions").  Costs one small launch per cycle.
+AUDIT = True
+NEAR_TIE = 1e-12
 
 
 class SweepState:
     """Device-resident state of a Jacobi optimisation: gamma, the 2-RDM (materialised or deferred), U."""
 
-    def __init__(self, g, G, Ud, n, inactive_indices, engine=None):
+    def __init__(self, g, G, Ud, n, inactive_indices, engine=None, audit=None):
         self.g, self.G, self.U, self.n = g, G, Ud, n
         self.engine = engine or ENGINE
+        if self.engine not in ('deferred', 'deferred-barrier', 'materialized'):
+            raise ValueError(f'unknown sweep engine {self.engine!r}')
+        self.audit = AUDIT if audit is None else audit
         self.mask = dev.inactive_mask(inactive_indices, n)
         self.inds = dev.to_device(np.asarray(list(inactive_indices), dtype=np.int32), dev.I32)
         self.tables = device_tables()
         self.W = None
-        if self.engine == 'deferred':
+        self.poisoned = False
+        self.last_audit = None
+        if self.engine != 'materialized':
             self.W = dev.empty(n, n)
             dev.sweep_reset(self.W, n)
 
-    def cycle(self, pairs_np):
+    def cycle(self, pairs_np, timers=False):
         """Run one cycle over ``pairs_np``. Returns (records, n_accepted, cost_after, flags)."""
+        if self.poisoned:
+            raise dev.QioCudaError('SweepState: an earlier cycle aborted half-way; the RDMs are inconsistent -- rebuild the state')
         n = self.n
         pairs = dev.to_device(pairs_np, dev.I32)
-        if self.engine == 'deferred':
-            results, summary = dev.sweep_cycle(self.g, self.G, self.U, self.W, n, pairs, self.mask, self.tables)
+        if self.engine != 'materialized':
+            blocks = dev.empty(max(len(pairs_np), 1), dev.BLOCK_DOUBLES) if self.audit else None
+            results, summary = dev.sweep_cycle(self.g, self.G, self.U, self.W, n, pairs, self.mask, self.tables,
+                                               engine=2 if self.engine == 'deferred-barrier' else 0, timers=timers,
+                                               blocks_out=blocks)
             diag = dev.deferred_diagonals(self.g, self.G, self.W, n, self.inds)
             _, _, _, esum = dev.orbital_entropies(diag, want_spec=False)
             dev.zero_offspin_if_rotated(self.g, n, summary)
             summ_h = dev.to_host(summary)
-            dev.check_sweep_summary(summ_h)
+            self.last_summary = summ_h
+            try:
+                dev.check_sweep_summary(summ_h)
+            except dev.QioCudaError:
+                self.poisoned = True
+                raise
             n_acc, _, flags = summ_h[:3]
             cost, _, _, eflags = dev.to_host(esum)
             flags = int(flags) | int(eflags)
-        else:
-            results, summary = dev.jacobi_cycle(self.g, self.G, self.U, n, pairs, self.mask, self.tables)
-            n_acc, cost, flags, _ = dev.to_host(summary)
+            rec = dev.results_to_numpy(results)
+            if self.audit:
+                self.last_audit = dev.audit_decisions(rec, blocks, pairs, self.mask, self.tables, NEAR_TIE)
+                report_audit(self.last_audit, pairs_np)
+            return rec, int(n_acc), float(cost), int(flags)
+        results, summary = dev.jacobi_cycle(self.g, self.G, self.U, n, pairs, self.mask, self.tables)
+        n_acc, cost, flags, _ = dev.to_host(summary)
         return dev.results_to_numpy(results), int(n_acc), float(cost), int(flags)
 
     def finish(self, work=None):
         """Materialise the 2-RDM (applies the pending rotation of the deferred engine)."""
-        if self.engine == 'deferred':
+        if self.poisoned:
+            raise dev.QioCudaError('SweepState: an earlier cycle aborted half-way; refusing to materialise inconsistent RDMs')
+        if self.engine != 'materialized':
             dev.sweep_flush(self.G, self.W, self.n, work)
         return self.g, self.G
+
+
+def report_audit(audit, pairs_np):
+    """Raises on a decision that the strict-order re-evaluation contradicts outside rounding; logs near-ties."""
+    if audit['unexplained']:
+        k = audit['unexplained'][0]
+        raise dev.QioCudaError(
+            f"sweep decision audit: {len(audit['unexplained'])} line-search decision(s) differ from the strict-order "
+            f"re-evaluation of the same pair block although no margin is below {NEAR_TIE:g} (first: pair #{k} = "
+            f"{tuple(int(x) for x in pairs_np[k])})")
+    if audit['near_ties']:
+        logger.info('note: %d line-search decisions closer than %g to a tie (%d of them decided differently by the '
+                    'strict-order re-evaluation); min margins: fine %.3e, coarse %.3e', len(audit['near_ties']), NEAR_TIE,
+                    len(audit['mismatches']), audit['min_fine_margin'], audit['min_coarse_margin'])
 
 
 def minimize_orb_corr_jacobi(gamma, Gamma, inactive_indices, max_cycle):
@@ -183,10 +232,6 @@ def minimize_orb_corr_jacobi(gamma, Gamma, inactive_indices, max_cycle):
             rotations.append([int(i) + 1, int(j) + 1, t / np.pi * 180])
         if n_acc > 0:
             new_cost = cost_after
-        low = rec['fine_margin'][np.isfinite(rec['fine_margin'])]
-        if low.size and low.min() < 1e-12:
-            logger.info('note: %d line-search decisions closer than 1e-12 to the acceptance margin',
-                        int((low < 1e-12).sum()))
         tol = CYCLE_TOL
         if cycle_cost - new_cost < tol:
             logger.info('reached tol = %s', tol)

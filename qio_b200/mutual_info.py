@@ -38,12 +38,17 @@ def orbital_entropies(gamma, Gamma):
 
 
 def mutual_information(gamma, Gamma, supplement=None):
-    """(n, n) symmetric matrix I_ij = S_i + S_j - S_ij with zero diagonal."""
+    """(n, n) symmetric matrix I_ij = S_i + S_j - S_ij with zero diagonal, assembled on the device.
+    ``supplement``: optional (n(n-1)/2, 9) array of the 3- / 4-body expectation values per pair, pairs in the order of
+    ``all_pairs(n)`` (what an extended solver's ``make_pair_supplement()`` returns, see qio_b200.qio.QIO)."""
     n = int(Gamma.shape[0])
-    S1 = np.asarray(dev.to_host(orbital_entropies(dev.to_device(gamma), dev.to_device(Gamma))))
-    S2, _, pairs = pair_entropies(dev.to_device(gamma), dev.to_device(Gamma), None, supplement)
-    S2 = dev.to_host(S2)
-    I = np.zeros((n, n))
-    i, j = pairs[:, 0], pairs[:, 1]
-    I[i, j] = I[j, i] = S1[i] + S1[j] - S2
-    return I
+    g, G = dev.to_device(gamma), dev.to_device(Gamma)
+    pairs_np = all_pairs(n)
+    pairs = dev.to_device(pairs_np, dev.I32)
+    blocks = dev.pair_blocks(g, G, n, pairs)
+    supp = None if supplement is None else dev.to_device(np.asarray(supplement, dtype=np.float64).reshape(len(pairs_np), N_SUPPLEMENT))
+    s_pair, _, _ = dev.pair_entropy(blocks, supp)
+    diag = dev.orbital_diagonals(g, G, n, dev.to_device(np.arange(n, dtype=np.int32), dev.I32))
+    _, s1, _, _ = dev.orbital_entropies(diag, want_spec=False)
+    I = dev.mutual_information_matrix(s1, s_pair, pairs, n)
+    return dev.like_input(I, Gamma)

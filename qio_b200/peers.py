@@ -24,11 +24,13 @@ class PeerGroup:
         self.group = group
         self.rank = dist.get_rank(group)
         self.nranks = dist.get_world_size(group)
-        nbytes = int(lib.qio_b200_mailbox_bytes(self.nranks))
+        nbytes = max(int(lib.qio_b200_mailbox_bytes(self.nranks)), int(lib.qio_b200_ll_stress_bytes(self.nranks)))
         own = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
         check(lib.qio_b200_ipc_alloc(nbytes, ctypes.byref(own), handle), 'ipc_alloc')
         self._own = own
+        self._nbytes = nbytes
+        self.wraps = 0
         handles = [None] * self.nranks
         dist.all_gather_object(handles, bytes(handle.raw), group=group)
         self._opened = []
@@ -45,9 +47,31 @@ class PeerGroup:
         self.struct = Peers(self.rank, self.nranks, 0, 0, self.ptr_table.data_ptr())
         dist.barrier(group=group)
 
+    EPOCHS = 4095           # 12 tag bits (csrc/ll.cuh); 0 is never used
+
     def next_epoch(self):
-        """Called once per sweep_cycle launch (identically on every rank)."""
-        self.struct.epoch = (self.struct.epoch + 1) & 0xffffffff
+        """Called once per sweep_cycle launch (identically on every rank).  The epoch distinguishes the launches in the
+        mailbox tags; before a value is reused every rank zeroes its own mailbox, fenced by two barriers."""
+        e = self.struct.epoch + 1
+        if e > self.EPOCHS:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)          # nobody is still writing into anybody's mailbox
+            check(lib.qio_b200_ipc_clear(self._own, self._nbytes, None), 'ipc_clear')
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            e = 1
+            self.wraps += 1
+        self.struct.epoch = e
+
+    def stress(self, iterations=4000, lanes=256):
+        """Self-test of the mailbox signalling: iterations x lanes tagged 16-byte stores from every rank into every
+        rank's mailbox, every received payload verified.  Collective.  Returns (mismatches, timeouts, words_checked)."""
+        self.next_epoch()
+        res = torch.zeros(3, dtype=torch.int64, device='cuda')
+        check(lib.qio_b200_ll_stress(ctypes.byref(self.struct), int(iterations), int(lanes), res.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream), 'll_stress')
+        bad, lost, seen = (int(x) for x in res.cpu())
+        return bad, lost, seen
 
     def close(self):
         torch.cuda.synchronize()

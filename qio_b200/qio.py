@@ -28,6 +28,12 @@ class QIO:
             max_cycle, thresh, level_shift, step_size, mu, mu_rate, debug, verbose
         Saved results: mo_coeff, gamma, Gamma, s_val, occ_num.
         Extra: keep_on_device (default False) leaves gamma / Gamma as CUDA tensors after kernel().
+        Extension (no reference counterpart): with ``compute_mutual_info = True`` kernel() also
+        stores the orbital mutual-information matrix of the solver's state, in the orbital basis it was given, in
+        ``self.mutual_info``; a solver that can supply the 3- / 4-body expectation values of every orbital pair does so
+        through an optional ``make_pair_supplement()`` -> (n(n-1)/2, 9) method next to make_rdm1 / make_rdm2 (pairs in the
+        order i > j, k = i(i-1)/2 + j; the nine numbers are listed in qio_b200/csrc/mi_formulas.inc).  Without it the
+        two-orbital RDMs are closed with the 2-body data only (exact for two-electron states).
         """
         self.mf = mf
         self.no = len(mf.mo_coeff)
@@ -49,6 +55,8 @@ class QIO:
         self.Gamma = None
         self.verbose = mf.verbose
         self.keep_on_device = False
+        self.compute_mutual_info = False
+        self.mutual_info = None
 
         if logger is not None:
             self.logger = logger
@@ -103,6 +111,12 @@ class QIO:
 
         gamma, Gamma = prep_rdm12(dm1, dm2, on_device=True)
 
+        if self.compute_mutual_info:
+            from .mutual_info import mutual_information
+            make_supp = getattr(self.sol, 'make_pair_supplement', None)
+            supp = make_supp() if callable(make_supp) else None
+            self.mutual_info = dev.to_host(mutual_information(gamma, Gamma, supp))
+
         if m in ('2D_JACOBI', '2DJACOBI', 'JACOBI'):
             _, U, g, G = minimize_orb_corr_jacobi(gamma, Gamma, inactive_indices, self.max_cycle)
         else:
@@ -121,13 +135,14 @@ class QIO:
         return self.mo_coeff
 
 
-def upload_and_prep_rdm2(dm2, n: int, a0: int = 0, na: int | None = None, slabs_per_chunk: int | None = None):
+def upload_and_prep_rdm2(dm2, n: int, a0: int = 0, na: int | None = None, slabs_per_chunk: int | None = None, out=None):
     """Host dm2[a0:a0+na] -> device Gamma[a0:a0+na] without ever holding the raw dm2 on the device:
     slabs of the leading index go through two pinned staging buffers on a copy stream while the prep
-    kernel of the previous chunk runs (both permutations keep the leading index)."""
+    kernel of the previous chunk runs (both permutations keep the leading index).
+    ``out``: optional preallocated (na, n, n, n) device tensor that receives Gamma."""
     d = dev.require_cuda()
     na = n - a0 if na is None else na
-    Gamma = dev.empty(na, n, n, n)
+    Gamma = dev.empty(na, n, n, n) if out is None else out
     if na == 0:
         return Gamma
     slab = n ** 3

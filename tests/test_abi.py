@@ -37,7 +37,19 @@ def test_struct_layouts_match():
     assert _lib.LS_DTYPE.itemsize == 80
     assert _lib.LS_DTYPE.fields['theta'][1] == 16 and _lib.LS_DTYPE.fields['cos_theta'][1] == 56
     assert ctypes.sizeof(_lib.ThetaTables) == 8 + 5 * 8
-    assert _lib.lib.qio_b200_abi_version() == 1
+    assert ctypes.sizeof(_lib.SweepOptions) == 4 * 4 + 8 and _lib.SweepOptions.blocks_out.offset == 16
+    assert ctypes.sizeof(_lib.Peers) == 4 * 4 + 8
+    assert _lib.lib.qio_b200_abi_version() == 2
+
+
+def test_library_keeps_no_process_state():
+    """The header promises a stateless ABI: no environment switches and no launch counters in the sources."""
+    csrc = os.path.join(ROOT, 'qio_b200', 'csrc')
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith(('.cu', '.cuh')):
+            src = open(os.path.join(csrc, f)).read()
+            assert 'getenv' not in src, f'{f} reads the environment'
+            assert 'launch_counter' not in src, f'{f} keeps a launch counter'
 
 
 def test_no_cpu_fallback():

@@ -309,16 +309,14 @@ def test_deferred_engine_matches_materialized_engine(n):
     pairs = JA.sweep_pairs(order, inact)
     out = {}
     for engine in ('materialized', 'deferred', 'deferred-barrier'):
-        if engine == 'deferred-barrier':
-            os.environ['QIO_B200_SWEEP_ENGINE'] = '2'
-        try:
-            gd, Gd, Ud = dev.to_device(g).clone(), dev.to_device(G).clone(), dev.to_device(np.eye(n)).clone()
-            st = JA.SweepState(gd, Gd, Ud, n, inact, engine=engine.split('-')[0])
-            rec1, acc1, cost1, _ = st.cycle(pairs)
-            rec2, acc2, cost2, _ = st.cycle(pairs[::-1].copy())          # second cycle on the deferred state
-            gg, GG = st.finish()
-        finally:
-            os.environ.pop('QIO_B200_SWEEP_ENGINE', None)
+        gd, Gd, Ud = dev.to_device(g).clone(), dev.to_device(G).clone(), dev.to_device(np.eye(n)).clone()
+        st = JA.SweepState(gd, Gd, Ud, n, inact, engine=engine)
+        rec1, acc1, cost1, _ = st.cycle(pairs)
+        rec2, acc2, cost2, _ = st.cycle(pairs[::-1].copy())          # second cycle on the deferred state
+        if engine != 'materialized':
+            assert st.last_audit['pairs'] == len(pairs) and not st.last_audit['unexplained']
+            assert st.last_summary[24] == (3.0 if engine == 'deferred' else 0.0)      # which kernel really ran
+        gg, GG = st.finish()
         out[engine] = (rec1, rec2, cost1, cost2, dev.to_host(gg), dev.to_host(GG), dev.to_host(Ud))
     # the pipelined and the barrier kernel sum the same partial products in different orders: same decisions
     c = out['deferred-barrier']
@@ -350,17 +348,13 @@ def test_partial_pair_list_pipelined_matches_barrier_kernel(n, K):
     pairs = JA.sweep_pairs(order, inact)[:K]
     out = {}
     for eng in ('3', '2'):
-        os.environ['QIO_B200_SWEEP_ENGINE'] = eng
-        try:
-            gd, Gd, Ud = dev.to_device(g).clone(), dev.to_device(G).clone(), dev.to_device(np.eye(n)).clone()
-            W = dev.empty(n, n)
-            dev.sweep_reset(W, n)
-            res, summ = dev.sweep_cycle(gd, Gd, Ud, W, n, dev.to_device(pairs, dev.I32), dev.inactive_mask(inact, n),
-                                        tables.device_tables())
-            dev.check_sweep_summary(dev.to_host(summ))
-            out[eng] = (dev.results_to_numpy(res), dev.to_host(Gd), dev.to_host(gd), dev.to_host(Ud), dev.to_host(W))
-        finally:
-            os.environ.pop('QIO_B200_SWEEP_ENGINE', None)
+        gd, Gd, Ud = dev.to_device(g).clone(), dev.to_device(G).clone(), dev.to_device(np.eye(n)).clone()
+        W = dev.empty(n, n)
+        dev.sweep_reset(W, n)
+        res, summ = dev.sweep_cycle(gd, Gd, Ud, W, n, dev.to_device(pairs, dev.I32), dev.inactive_mask(inact, n),
+                                    tables.device_tables(), engine=int(eng))
+        dev.check_sweep_summary(dev.to_host(summ))
+        out[eng] = (dev.results_to_numpy(res), dev.to_host(Gd), dev.to_host(gd), dev.to_host(Ud), dev.to_host(W))
     assert dev.sweep_engine(n) == 3
     a, b = out['3'], out['2']
     assert np.array_equal(a[0]['accepted'], b[0]['accepted'])
@@ -373,13 +367,7 @@ def test_partial_pair_list_pipelined_matches_barrier_kernel(n, K):
 @pytest.mark.parametrize('engine', ['deferred', 'deferred-barrier', 'materialized'])
 def test_jacobi_driver_golden_rotations_bit_exact(golden, engine, monkeypatch):
     """'deferred' = the pipelined kernel (sweep3.cu), 'deferred-barrier' = the same state with one grid barrier per pair
-    (sweep2.cu, forced through the environment switch), 'materialized' = one launch per pair on the natural layout."""
-    if engine == 'deferred-barrier':
-        monkeypatch.setenv('QIO_B200_SWEEP_ENGINE', '2')
-        engine = 'deferred'
-        assert dev.sweep_engine(int(golden['n'])) == 2
-    else:
-        monkeypatch.delenv('QIO_B200_SWEEP_ENGINE', raising=False)
+    (sweep2.cu, forced through the options of the call), 'materialized' = one launch per pair on the natural layout."""
     monkeypatch.setattr(JA, 'ENGINE', engine)
     gamma0, Gamma0 = prepared_inputs(golden)
     n = int(golden['n'])

@@ -28,6 +28,20 @@ def test_shard_ranges_cover_and_balance():
     assert lo_hi[0][0] == 0 and lo_hi[-1][1] == 4950 and all(lo_hi[r][1] == lo_hi[r + 1][0] for r in range(7))
 
 
+def test_reshard_capacity_covers_both_layouts():
+    for n, world in ((7, 2), (100, 8), (200, 8), (13, 4)):
+        cap = sharded.reshard_capacity(n, world)
+        na_max = max(sharded.shard_range(n, r, world)[1] - sharded.shard_range(n, r, world)[0] for r in range(world))
+        assert cap >= na_max * n ** 3 and cap >= n * max(sharded.column_splits(n ** 3, world)[1])
+        assert cap <= (na_max + 1) * n ** 3          # never anywhere near the full n^4 tensor
+    # single rank: the "re-shard" is the plain contraction
+    n = 4
+    X = torch.arange(n * n ** 3, dtype=torch.float64).reshape(n, -1)
+    M = torch.eye(n, dtype=torch.float64) * 2
+    out = sharded.apply_leading_alltoall(lambda c, o: o.copy_(M @ c), X.reshape(-1).clone(), torch.empty(n * n ** 3, dtype=torch.float64), n, [n], 0)
+    assert torch.equal(out, 2 * X)
+
+
 def test_all_pairs_order_is_the_reference_loop_order():
     n = 9
     want = [(i, j) for i in range(n) for j in range(i)]
@@ -95,6 +109,26 @@ def _worker(rank, world, port, n):
         t = torch.from_numpy(emulated_partial_blocks(gamma, Gamma, pairs, a0, a1))
         sharded.allreduce_sum_(t)
         assert np.array_equal(t.numpy(), emulated_partial_blocks(gamma, Gamma, pairs, 0, n))
+        # leading-axis contraction by re-sharding to columns (all-to-all), local GEMM, re-sharding back
+        gen = torch.Generator().manual_seed(11)
+        n3 = n ** 3
+        X = torch.randn((n, n3), dtype=torch.float64, generator=gen)
+        M = torch.randn((n, n), dtype=torch.float64, generator=gen)
+        cap = sharded.reshard_capacity(n, world)
+        local = torch.zeros(cap, dtype=torch.float64)
+        local[:(a1 - a0) * n3] = X[a0:a1].reshape(-1)
+        scratch = torch.full((cap,), float('nan'), dtype=torch.float64)
+        seen = []
+
+        def gemm(cols, out):
+            seen.append(tuple(cols.shape))
+            out.copy_(M @ cols)
+
+        got = sharded.apply_leading_alltoall(gemm, local, scratch, n, counts, rank)
+        assert got.shape == (a1 - a0, n3) and got.data_ptr() == scratch.data_ptr()
+        assert torch.allclose(got, (M @ X)[a0:a1], atol=1e-13, rtol=0)
+        lo, width = sharded.column_splits(n3, world)
+        assert seen == [(n, width[rank])] and lo[0] == 0 and lo[-1] == n3 and sum(width) == n3
         # sharded one-orbital cost: owners contribute Gamma[k,k,k,k], sum, then the replicated entropy
         k = np.arange(n)
         nn = torch.from_numpy(np.where((k >= a0) & (k < a1), Gamma[k, k, k, k], 0.0))
