@@ -1,28 +1,40 @@
 #!/usr/bin/env python
 """Benchmark of the QIO orbital-entropy hot path on B200 (contract: see the task statement / DESIGN.md).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 100] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--orbitals 100] [--impl reference] [--no-north-star]
 
 One "step" is one complete pass of the hot path over one synthetic solver output:
 
     prep_rdm12(dm1, dm2)                        a-1   (restores the pristine RDMs every step)
     random-start orbital rotation (2- and 4-index, FP64 DMMA)   a-7 start / a-10 rotation
-    all-pairs pass: pair blocks, gradient + Hessian, angle line search for all n(n-1)/2 pairs   a-8, a-5
-    one full Jacobi cycle: 4950 (n=100) sequential line searches + Givens updates of the RDMs   a-7, a-6
-    get_cost_fqi of the result                   a-3
+    all-pairs pass: pair blocks, gradient + Hessian, angle line search for all n(n-1)/2 pairs, pair entropies and the
+        mutual-information matrix                                                           a-8, a-5, a-9
+    one full Jacobi cycle: 4950 (n=100) sequential line searches + Givens updates of the RDMs, followed by the
+        strict-order audit of every decision                                                a-7, a-6
+    get_cost_fqi of the result, flush of the deferred state      a-3
 
 metric  = orbital-pair entropy evaluations (jacobi_cost calls of the reference) per second over the step;
 ms_per_step is the wall time of the whole step (all-pairs pass + Jacobi sweep).
 `value`: inputs (dm1, dm2, start rotation, pair order) resident in HBM.   `e2e`: the same step through the
 public Python API from pinned HOST buffers, H2D of dm1/dm2 and D2H of the results inside the timed region.
+`north_star`: the same two measurements on BASELINE.json configs[4] (n = 200), at whatever GPU count the run has.
 """
 from __future__ import annotations
 
-import argparse
-import json
 import os
-import subprocess
 import sys
+
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # The CPU arm uses every host core for its BLAS part whatever the launcher exported (torchrun sets
+    # OMP_NUM_THREADS=1 for its children): fix the thread counts BEFORE numpy loads its BLAS.
+    _cores = str(os.cpu_count() or 1)
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = _cores
+
+import argparse
+import importlib.util
+import json
+import subprocess
 import threading
 import time
 
@@ -33,6 +45,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'orbital_pair_entropy_evals_per_s'
 UNIT = 'evals/s'
+NORTH_STAR_N = 200
 
 
 def parse_args():
@@ -42,11 +55,22 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=3)
     # '--orbitals' is the spelling to use under torchrun: its own parser rejects '--n' as an ambiguous prefix
     ap.add_argument('--n', '--orbitals', dest='n', type=int, default=int(os.environ.get('QIO_BENCH_N', '100')),
-                    help='number of orbitals (100 = configs[3], 200 = configs[4])')
+                    help='number of orbitals of the headline leg (100 = configs[3])')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-north-star', action='store_true', help='skip the second leg on configs[4] (n = 200)')
+    ap.add_argument('--no-parity', action='store_true', help='N > 1: skip the sharded-vs-single-GPU self-check')
     return ap.parse_args()
+
+
+def load_synth():
+    """qio_b200/synth.py as a stand-alone module: plain numpy, and importing it this way does not load the CUDA library
+    (the reference arm must not map the product's .so)."""
+    spec = importlib.util.spec_from_file_location('qio_b200_synth_standalone', os.path.join(ROOT, 'qio_b200', 'synth.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 # --------------------------------------------------------------------------------------------------
@@ -55,7 +79,7 @@ def parse_args():
 def workload_config(n, n_gpus):
     return {
         'workload': f'synthetic determinant-ensemble rdm1/rdm2, n={n} orbitals (K=4, nocc={max(1, n // 5)}, seed 20261019+n), '
-                    f'inactive = all orbitals: prep_rdm12 + random-start rotation + all-pairs grad/Hess/line-search/pair-entropy '
+                    f'inactive = all orbitals: prep_rdm12 + random-start rotation + all-pairs grad/Hess/line-search/mutual-information '
                     f'+ one full Jacobi cycle',
         'n_orbitals': n,
         'pairs': n * (n - 1) // 2,
@@ -75,6 +99,13 @@ def sweep_order(n):
     order = np.arange(0, n)
     np.random.shuffle(order)
     return U0, order
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
 # --------------------------------------------------------------------------------------------------
@@ -132,16 +163,35 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on the host cores
+# reference arm / cpu baseline: the reference's own CPU implementation on the host cores
 # --------------------------------------------------------------------------------------------------
 _CPU_SETUP = {}
 
 
+def cpu_functions():
+    """(kind, line search, transform, prepared-RDM rotation helpers).  'reference' = the unmodified reference package copied
+    to oracle/_ref by oracle/make_ref.py; 'port' = the oracle restatement (only when that copy does not exist)."""
+    from oracle import make_ref
+    from oracle import qio_oracle as O
+    ref = make_ref.load_reference()
+    if ref is not None:
+        return 'reference', ref['jacobi'].jacobi_direct, ref['jacobi'].jacobi_transform, O
+    return 'port', O.jacobi_direct_scalar, O.jacobi_transform_dense, O
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(p.get('num_threads', 1)) for p in threadpool_info() if p.get('user_api') == 'blas'] or [1])
+    except Exception:       # noqa: BLE001 (diagnostic only)
+        return None
+
+
 def cpu_reference_setup(n):
-    """Rotated synthetic RDMs and the sweep pair order on the host (built once per process)."""
+    """Rotated synthetic RDMs and the sweep pair order on the host (built once per process; plain numpy)."""
     if n not in _CPU_SETUP:
         from oracle import qio_oracle as O
-        from qio_b200 import synth
+        synth = load_synth()
         t0 = time.time()
         gamma0, Gamma0 = synth.prepared_rdms(n)
         U0, order = sweep_order(n)
@@ -153,36 +203,39 @@ def cpu_reference_setup(n):
 
 
 def cpu_reference_sample(n, n_ls_pairs=48, n_sweep_pairs=4, offset=0):
-    """Times the reference-shaped CPU path (oracle port: scalar jacobi_cost loop for the line search, dense
-    einsum for jacobi_transform -- what qio/grad/jacobi.py executes) on a bounded sample and extrapolates the
-    evals/s of the full step:  all-pairs pass = P line searches;  sweep = P x (line search + accepted transform)."""
-    from oracle import qio_oracle as O
+    """Times the reference's CPU path (qio/grad/jacobi.py: the pure-Python jacobi_cost loop of jacobi_direct and the dense
+    einsum of jacobi_transform) on a bounded sample and extrapolates the evals/s of the full step:
+    all-pairs pass = P line searches;  sweep = P x (line search + accepted transform)."""
+    kind, line_search, transform, _ = cpu_functions()
     st = cpu_reference_setup(n)
     g, G, inact, pairs = st['g'], st['G'], st['inact'], st['pairs']
     P = len(pairs)
     sample = [pairs[(offset + k) % P] for k in range(n_ls_pairs)]
-    # line searches (1 core, pure Python like the reference)
+    # line searches (1 core: pure Python in the reference)
     t0 = time.time()
-    thetas = [O.jacobi_direct_scalar(i, j, g, G, inact) for (i, j) in sample]
+    thetas = [line_search(i, j, g, G, inact) for (i, j) in sample]
     t_ls = (time.time() - t0) / n_ls_pairs
     accepted = sum(t is not None for t in thetas)
     # dense transforms (BLAS threads)
     t0 = time.time()
     done = 0
     for (i, j), t in zip(sample[:n_sweep_pairs], thetas[:n_sweep_pairs]):
-        O.jacobi_transform_dense(g, G, i, j, 0.1 if t is None else t)
+        transform(g, G, i, j, 0.1 if t is None else t)
         done += 1
     t_tr = (time.time() - t0) / max(done, 1)
     acc_rate = accepted / n_ls_pairs
     evals_per_pair = 515.5
     step_s = P * t_ls + P * (t_ls + acc_rate * t_tr)
     value = 2 * P * evals_per_pair / step_s
+    nblas = blas_threads()
+    what = ("the reference's own qio.grad.jacobi (unmodified copy under oracle/_ref)" if kind == 'reference'
+            else 'oracle port of the reference CPU path (oracle/_ref missing)')
     return {
-        'value': value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
-        'sample': (f'oracle port of the reference CPU path at n={n}: {n_ls_pairs} scalar line searches '
-                   f'({t_ls * 1e3:.1f} ms each, 1 core) + {done} dense jacobi_transform einsums ({t_tr:.2f} s each, '
-                   f'BLAS on {os.cpu_count()} cores); full step extrapolated as P*t_ls + P*(t_ls + {acc_rate:.2f}*t_tr) '
-                   f'= {step_s:.0f} s for P={P} pairs'),
+        'value': value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': kind, 'blas_threads': nblas,
+        'sample': (f'{what} at n={n}: {n_ls_pairs} jacobi_direct line searches '
+                   f'({t_ls * 1e3:.1f} ms each, 1 core, pure Python) + {done} jacobi_transform einsums ({t_tr:.2f} s each, '
+                   f'BLAS on {nblas} of {os.cpu_count()} host threads, OMP_NUM_THREADS={os.environ.get("OMP_NUM_THREADS", "unset")}); '
+                   f'full step EXTRAPOLATED as P*t_ls + P*(t_ls + {acc_rate:.2f}*t_tr) = {step_s:.0f} s for P={P} pairs'),
         'line_search_ms': t_ls * 1e3, 'transform_s': t_tr, 'extrapolated_step_s': step_s, 'setup_s': st['setup_s'],
     }
 
@@ -208,9 +261,12 @@ def run_reference_arm(args):
         'warmup': args.warmup, 'ms_per_step': last['extrapolated_step_s'] * 1e3, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args.n, args.gpus),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': last['cores'], 'kind': 'port', 'sample': last['sample']},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': last['cores'], 'kind': last['kind'], 'sample': last['sample'],
+                         'blas_threads': last['blas_threads']},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
+        'extrapolated': True,
+        'loaded_product_library': any('libqio_b200' in line for line in open('/proc/self/maps')),
     }
     print(json.dumps(out))
 
@@ -218,9 +274,43 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------
+def moved_bytes(n, na, pairs_np, accepted, look=3):
+    """Bytes the deferred layout really moves in the flat + tile phases of a cycle: per accepted rotation w the rows
+    (i|j, x) and (x, i|j) of every ACTIVE orbital x (one that has appeared in a super block <= w + look) over the na local
+    slabs, read + written: 2 axes x 2 rows x n_active x n x na x 8 B x 2."""
+    seen = np.zeros(n, dtype=bool)
+    active_at = np.empty(len(pairs_np), dtype=np.int64)
+    first = {}
+    for k, (i, j) in enumerate(pairs_np):
+        for x in (int(i), int(j)):
+            first.setdefault(x, k)
+    first_arr = np.array([first.get(x, 1 << 60) for x in range(n)])
+    for w in range(len(pairs_np)):
+        active_at[w] = int((first_arr <= w + look).sum())
+    acc = np.asarray(accepted, dtype=bool)
+    return float((2 * 2 * active_at[acc] * n * na * 8 * 2).sum())
+
+
+def count_launches(engine, world=1, audit=True):
+    """Kernels of THIS library launched by one device step (torch copies / NCCL calls are not counted)."""
+    c = 0
+    c += 2                  # prep_rdm12: 1-RDM interleave + 2-RDM permute/combine
+    c += 1 + (4 if world == 1 else 3 + 1)   # rotate_rdm1; rotate_rdm2: 4 passes, or 3 batched passes + the column-block GEMM
+    c += 1 + 1 + 1 + 1      # pair_blocks, grad/Hess, line search of all pairs, pair entropies
+    c += 1 + 1 + 1          # mutual-information matrix: diagonals, one-orbital entropies, assembly
+    c += 1                  # sweep_reset
+    c += 1 + (1 if engine == 3 else 0)      # sweep kernel (+ its per-pair table kernel)
+    c += 1 + 1 + 1          # deferred diagonals, entropies (cost), off-spin zeroing
+    c += 1 if audit else 0  # strict-order re-evaluation of every decision
+    c += 2 + 1              # flush: last-axis pass + leading-axis pass, W reset
+    return c
+
+
 def run_b200_arm(args):
-    if not os.environ.get('QIO_BENCH_KEEP_NCCL_DEBUG'):
-        os.environ['NCCL_DEBUG'] = 'WARN'       # keep NCCL's version banner off stdout: rank 0 prints one JSON line only
+    # NCCL's own log (communicator sizes, transports) goes to stderr, never to stdout: rank 0 prints one JSON line only
+    os.environ.setdefault('NCCL_DEBUG', 'INFO')
+    os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     import torch
     import torch.distributed as dist
 
@@ -231,19 +321,39 @@ def run_b200_arm(args):
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    if args.gpus != world and world > 1:
         args.gpus = world
+        return run_b200_multi(args, rank, world, local_rank)
+
+    out = single_gpu_leg(args, args.n, args.steps, max(args.warmup, 3), local_rank, detail=True)
+    if not args.no_north_star and args.n != NORTH_STAR_N:
+        torch.cuda.empty_cache()
+        ns = single_gpu_leg(args, NORTH_STAR_N, max(1, min(args.steps, 2)), 3, local_rank, detail=False)
+        out['north_star'] = north_star_record(ns)
+    print(json.dumps(out))
+
+
+def north_star_record(leg):
+    """BASELINE.json configs[4] as a sub-record of the JSON line."""
+    keep = ('ms_per_step', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'e2e', 'roofline', 'clocks', 'rotations_accepted',
+            'cost_after_cycle', 'decision_audit', 'phases', 'evals_per_step', 'peak_memory_gb')
+    rec = {k: leg.get(k) for k in keep}
+    rec['n'] = leg['config']['n_orbitals']
+    rec['config'] = leg['config']
+    rec['target'] = 'mutual-information matrix + one complete Jacobi sweep at n=200 in < 1 s on 8 B200 (BASELINE.json north_star)'
+    rec['meets_target_ms'] = bool(leg['ms_per_step'] < 1000.0)
+    return rec
+
+
+def single_gpu_leg(args, n, steps, warmup, local_rank, detail):
+    import torch
 
     from qio_b200 import device as dev
+    from qio_b200 import mutual_info as MI
     from qio_b200 import synth, tables
     from qio_b200._lib import LS_DTYPE
     from qio_b200.grad import jacobi as JA
     from qio_b200.qio import prep_rdm12
 
-    if world > 1:
-        return run_b200_multi(args, rank, world, local_rank)
-
-    n = args.n
     P = n * (n - 1) // 2
     inact = list(range(n))
     # ---- synthetic solver output on the host (pinned) and on the device ---------------------------
@@ -254,8 +364,10 @@ def run_b200_arm(args):
     wt = torch.from_numpy(w).cuda()
     dm1_d = torch.einsum('k,kab->ab', wt, d1).contiguous()
     dm2_d = torch.zeros((n, n, n, n), dtype=torch.float64, device='cuda')
-    for k in range(len(w)):     # input synthesis only (plumbing, outside every timed region)
-        dm2_d += wt[k] * (torch.einsum('pq,rs->pqrs', d1[k], d1[k]) - 0.5 * torch.einsum('ps,rq->pqrs', d1[k], d1[k]))
+    for k in range(len(w)):     # input synthesis only (plumbing, outside every timed region), slab-wise to bound the temporaries
+        for a0 in range(0, n, 25):
+            dl = d1[k][a0:a0 + 25]
+            dm2_d[a0:a0 + 25] += wt[k] * (torch.einsum('pq,rs->pqrs', dl, d1[k]) - 0.5 * torch.einsum('ps,rq->pqrs', dl, d1[k]))
     dm1_h.copy_(dm1_d)
     dm2_h.copy_(dm2_d)
     torch.cuda.synchronize()
@@ -275,8 +387,11 @@ def run_b200_arm(args):
     gamma = dev.empty(2 * n, 2 * n)
     work = dev.empty(n, n, n, n)
     W = dev.empty(n, n)
+    blocks_sweep = dev.empty(len(pairs_np), dev.BLOCK_DOUBLES)
     inds_d = dev.to_device(np.arange(n, dtype=np.int32), dev.I32)
     state = {}
+    engine = dev.sweep_engine(n)
+    torch.cuda.reset_peak_memory_stats()
 
     def device_step():
         """The whole hot path with every input already in HBM."""
@@ -286,15 +401,18 @@ def run_b200_arm(args):
         blocks = dev.pair_blocks(g, Gamma, n, allpairs_d)
         dX, ddX = dev.fqi_grad_hess(blocks, n, mask)
         ls_all = dev.pair_linesearch(blocks, allpairs_d, mask, tabs)
-        s_pair, _, _ = dev.pair_entropy(blocks)          # extension a-9: pair entropies for the mutual-information matrix
+        s_pair, _, _ = dev.pair_entropy(blocks)          # extension a-9: pair entropies ...
+        _, s1, _, _ = dev.orbital_entropies(dev.orbital_diagonals(g, Gamma, n, inds_d), want_spec=False)
+        mi = dev.mutual_information_matrix(s1, s_pair, allpairs_d, n)      # ... and the mutual-information matrix
         Ud = U0_d.clone()
         dev.sweep_reset(W, n)
-        res, summary = dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs)
+        res, summary = dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs, blocks_out=blocks_sweep)
+        strict = dev.pair_linesearch(blocks_sweep, pairs_d, mask, tabs, strict_order=True)      # decision audit
         diag = dev.deferred_diagonals(g, Gamma, W, n, inds_d)
         _, _, _, esum = dev.orbital_entropies(diag, want_spec=False)
         dev.zero_offspin_if_rotated(g, n, summary)
         dev.sweep_flush(Gamma, W, n, work)
-        state.update(ls_all=ls_all, res=res, summary=summary, esum=esum, U=Ud, dX=dX, g=g)
+        state.update(ls_all=ls_all, res=res, strict=strict, summary=summary, esum=esum, U=Ud, dX=dX, g=g, mi=mi)
 
     def count_evals():
         ra = dev.results_to_numpy(state['ls_all'])
@@ -308,17 +426,28 @@ def run_b200_arm(args):
         """The same step through the public API from pinned host buffers (e2e)."""
         g0, G0 = prep_rdm12(dm1_h.numpy(), dm2_h, on_device=True)
         rec_all = JA.linesearch_pairs(g0, G0, allpairs_np, inact)
+        mi = MI.mutual_information(g0, G0)
         np.random.seed(0)
-        rots, U, g1, G1 = JA.minimize_orb_corr_jacobi(g0, G0, inact, 1)
+        rots, U, g1, G1 = JA.minimize_orb_corr_jacobi(g0, G0, inact, 1)      # includes the decision audit (JA.AUDIT)
+        mi_h = dev.to_host(mi)
         torch.cuda.synchronize()
-        return rec_all, rots, U
+        return rec_all, rots, U, mi_h
 
     # ---- warm-up ------------------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         device_step()
     torch.cuda.synchronize()
+    dev.check_sweep_summary(dev.to_host(state['summary']))
     evals_per_step, n_accepted, rs = count_evals()
     cost_after = float(dev.to_host(state['esum'])[0])
+    audit = dev.audit_decisions(rs, blocks_sweep, pairs_d, mask, tabs)
+    decision_audit = {'pairs': audit['pairs'], 'mismatches': len(audit['mismatches']), 'near_ties_below_1e-12': len(audit['near_ties']),
+                      'unexplained': len(audit['unexplained']), 'min_fine_margin': audit['min_fine_margin'],
+                      'min_coarse_margin': audit['min_coarse_margin'],
+                      'how': 'every line-search decision of the cycle re-derived in the reference operation order (strict_order) from the '
+                             '24-number block the sweep kernel searched; same coarse and fine index required'}
+    if audit['unexplained']:
+        raise RuntimeError(f'decision audit failed: {audit["unexplained"][:5]}')
 
     # ---- timed: device-resident -----------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -327,19 +456,18 @@ def run_b200_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         device_step()
     e1.record()
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    ms_per_step = ms_total / args.steps
+    ms_per_step = ms_total / steps
     value = evals_per_step / (ms_per_step * 1e-3)
-    launches_per_step = 2 + 1 + 4 + 1 + 1 + 1 + 1 + (1 + 1 + 1 + 1 + 1) + 3   # prep, rotations, all-pairs (+MI), sweep (+cost), flush
-    if dev.sweep_engine(n) == 3:
-        launches_per_step += 1      # per-pair table kernel of the pipelined sweep
+    launches_per_step = count_launches(engine)
+    peak_mem = torch.cuda.max_memory_allocated() / 1e9
 
-    # ---- phase timings (explain the step) and the roofline of the dominant kernel ----------------------
+    # ---- phase timings (explain the step) and the rooflines -------------------------------------------------
     def timed(fn, reps=1):
         a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -350,6 +478,7 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
         return a_.elapsed_time(b_) / reps
 
+    peak, peak_src = hbm_peak()
     phases = {}
     phases['prep_rdm12_ms'] = timed(lambda: dev.prep_rdm12(dm1_d, dm2_d, n, gamma=gamma, Gamma=Gamma), 3)
     phases['rotate_rdm2_ms'] = timed(lambda: dev.rotate_rdm2_(U0_d, Gamma, n, work), 3)
@@ -358,52 +487,48 @@ def run_b200_arm(args):
     phases['pair_blocks_ms'] = timed(lambda: dev.pair_blocks(g, Gamma, n, allpairs_d), 5)
     phases['grad_hess_ms'] = timed(lambda: dev.fqi_grad_hess(blocks, n, mask), 5)
     phases['linesearch_all_pairs_ms'] = timed(lambda: dev.pair_linesearch(blocks, allpairs_d, mask, tabs), 5)
-    phases['pair_entropy_mi_ms'] = timed(lambda: dev.pair_entropy(blocks), 5)
-    Ud = U0_d.clone()
-    dev.sweep_reset(W, n)
-    sweep_ms = timed(lambda: dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs), 1)
-    phases['jacobi_cycle_kernel_ms'] = sweep_ms
-    rs2 = dev.results_to_numpy(dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs)[0])   # 3rd cycle: count below
-    phases['sweep_flush_ms'] = timed(lambda: dev.sweep_flush(Gamma, W, n, work), 1)
+    phases['pair_entropy_ms'] = timed(lambda: dev.pair_entropy(blocks), 5)
+    s_pair = dev.pair_entropy(blocks)[0]
+    phases['mutual_information_matrix_ms'] = timed(lambda: dev.mutual_information_matrix(
+        dev.orbital_entropies(dev.orbital_diagonals(g, Gamma, n, inds_d), want_spec=False)[1], s_pair, allpairs_d, n), 5)
+    phases['decision_audit_ms'] = timed(lambda: dev.pair_linesearch(blocks_sweep, pairs_d, mask, tabs, strict_order=True), 3)
     m1_evals = int((1 + 314 + fine_len[np.where(dev.results_to_numpy(state['ls_all'])['coarse_index'] >= 0,
                                                 dev.results_to_numpy(state['ls_all'])['coarse_index'], 0)]).sum())
     phases['all_pairs_evals_per_s'] = m1_evals / (phases['linesearch_all_pairs_ms'] * 1e-3)
 
-    # one Newton-Raphson ("nr", the path of the reference's examples) iteration through the public API, device-resident
-    # RDMs: grad/Hess kernels, D2H of two n x n matrices, host level shift + scipy expm, H2D of U, 4-index rotation, cost
-    from qio_b200.grad import gradient as GR
-    dev.prep_rdm12(dm1_d, dm2_d, n, gamma=gamma, Gamma=Gamma)
-    GR.minimize_orb_corr_GD(gamma, Gamma, inact, np.zeros(0, dtype=np.int64), max_cycle=1, thresh=0.0)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    GR.minimize_orb_corr_GD(gamma, Gamma, inact, np.zeros(0, dtype=np.int64), max_cycle=4, thresh=0.0)
-    torch.cuda.synchronize()
-    phases['gd_newton_iteration_ms'] = (time.perf_counter() - t0) * 1e3 / 4
+    # dominant kernel = the persistent sweep kernel, timed alone on the step's own first cycle (same start state)
+    def fresh_state():
+        dev.prep_rdm12(dm1_d, dm2_d, n, gamma=gamma, Gamma=Gamma)
+        g_ = dev.rotate_rdm1(U0_d, gamma, n)
+        dev.rotate_rdm2_(U0_d, Gamma, n, work)
+        dev.sweep_reset(W, n)
+        return g_, U0_d.clone()
 
-    # dominant kernel = the persistent sweep kernel.  Timed alone on the step's own first cycle (same start state).
-    dev.prep_rdm12(dm1_d, dm2_d, n, gamma=gamma, Gamma=Gamma)
-    g = dev.rotate_rdm1(U0_d, gamma, n)
-    dev.rotate_rdm2_(U0_d, Gamma, n, work)
-    Ud = U0_d.clone()
-    dev.sweep_reset(W, n)
+    g, Ud = fresh_state()
     sweep_ms = timed(lambda: dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs), 1)
-    phases['jacobi_cycle_kernel_first_cycle_ms'] = sweep_ms
-    os.environ['QIO_B200_SWEEP_TIMERS'] = '1'       # the build of the sweep kernel that carries its phase timers (about 5 % slower)
-    tsum = dev.to_host(dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs)[1])
-    os.environ.pop('QIO_B200_SWEEP_TIMERS', None)
-    phases['sweep_phase_us_per_pair'] = sweep_phase_table(tsum, len(pairs_np))
-    lsn = ['coarse', 'reduce', 'fine', 'scan', 'margin', 'tail']
-    phases['linesearch_cycles_per_pair_cta0'] = {k: float(v) / len(pairs_np) for k, v in zip(lsn, tsum[10:16])}
-    algo_bytes = 16.0 * (n ** 4 - (n - 2) ** 4) * n_accepted      # bytes the reference update touches
-    kernel_bytes = 64.0 * n ** 3 * n_accepted + 32.0 * n * n * len(pairs_np)   # what the deferred layout moves
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(peaks_path):
-        peak = json.load(open(peaks_path))['hbm_gbs']
-        peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)'
-    else:
-        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    phases['jacobi_cycle_kernel_ms'] = sweep_ms
+    phases['sweep_flush_ms'] = timed(lambda: dev.sweep_flush(Gamma, W, n, work), 1)
+    if detail:
+        g, Ud = fresh_state()
+        tsum = dev.to_host(dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs, timers=True)[1])   # build with phase timers (~5 % slower)
+        phases['sweep_phase_us_per_pair'] = sweep_phase_table(tsum, len(pairs_np))
+        lsn = ['coarse', 'reduce', 'fine', 'scan', 'margin', 'tail']
+        phases['linesearch_cycles_per_pair_cta0'] = {k: float(v) / len(pairs_np) for k, v in zip(lsn, tsum[10:16])}
+        # one Newton-Raphson ("nr", the path of the reference's examples) iteration through the public API, device-resident
+        # RDMs: grad/Hess kernels, D2H of two n x n matrices, host level shift + scipy expm, H2D of U, 4-index rotation, cost
+        from qio_b200.grad import gradient as GR
+        dev.prep_rdm12(dm1_d, dm2_d, n, gamma=gamma, Gamma=Gamma)
+        GR.minimize_orb_corr_GD(gamma, Gamma, inact, np.zeros(0, dtype=np.int64), max_cycle=1, thresh=0.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        GR.minimize_orb_corr_GD(gamma, Gamma, inact, np.zeros(0, dtype=np.int64), max_cycle=4, thresh=0.0)
+        torch.cuda.synchronize()
+        phases['gd_newton_iteration_ms'] = (time.perf_counter() - t0) * 1e3 / 4
+
+    acc_mask = rs['accepted'] != 0
+    algo_bytes = 16.0 * (n ** 4 - (n - 2) ** 4) * n_accepted      # bytes the reference's update touches
+    moved = moved_bytes(n, n, pairs_np, acc_mask)                 # what the deferred layout with dormant-row skipping moves
     achieved = algo_bytes / (sweep_ms * 1e-3) / 1e9
-    engine = dev.sweep_engine(n)
     kname = ('sweep3_kernel (pipelined persistent Jacobi cycle: search CTA + reducers + column-owning workers)' if engine == 3
              else 'sweep_kernel (persistent Jacobi cycle, one grid barrier per pair)')
     traffic, traffic_src = None, None
@@ -417,12 +542,26 @@ def run_b200_arm(args):
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'peak_source': peak_src, 'traffic': traffic, 'traffic_source': traffic_src, 'algorithmic_bytes_per_launch': algo_bytes,
                 'avg_launch_ms': sweep_ms, 'launches_timed': 1,
-                'kernel_min_bytes_per_launch': kernel_bytes,
-                'kernel_min_bytes_frac': kernel_bytes / (sweep_ms * 1e-3) / 1e9 / peak,
-                'note': 'algorithmic bytes = 16 (n^4-(n-2)^4) per accepted rotation (SURVEY 8d); the deferred-axis layout '
-                        'moves only 64 n^3 B per rotation (+ 32 n^2 B of block rows per pair), see kernel_min_bytes_*; '
-                        'per-rotation working set %.0f MB vs 126 MB L2 (L2-resident: DRAM traffic below the algorithmic bytes, '
-                        'frac above 1 is possible)' % (32.0 * n ** 3 / 1e6)}
+                'moved_bytes_per_launch': moved,
+                'frac_moved': moved / (sweep_ms * 1e-3) / 1e9 / peak,
+                'frac_dram': (traffic / (sweep_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                'note': 'achieved / frac follow the contract: ALGORITHMIC bytes = 16 (n^4-(n-2)^4) per accepted rotation, the '
+                        "reference's own touch count (SURVEY 8d) -- an effective bandwidth, it exceeds 1 when the layout moves fewer "
+                        'bytes than the reference touches.  frac_moved = bytes the deferred-axis layout with dormant-row skipping really '
+                        'reads + writes (64 n^2 n_active per rotation) / time / peak; frac_dram = DRAM bytes of the committed ncu capture '
+                        '/ time / peak = the true HBM fraction.  Per-rotation working set %.0f MB vs 126 MB L2.' % (32.0 * n ** 3 / 1e6)}
+
+    # the other two kernels north_star names: prep_rdm12 (HBM-bound) and the 4-index rotation (FP64 tensor pipe)
+    prep_bytes = 16.0 * n ** 4
+    roofline_prep = {'kernel': 'prep_rdm2_kernel', 'bound': 'hbm', 'achieved': prep_bytes / (phases['prep_rdm12_ms'] * 1e-3) / 1e9,
+                     'peak': peak, 'unit': 'GB/s', 'frac': prep_bytes / (phases['prep_rdm12_ms'] * 1e-3) / 1e9 / peak,
+                     'algorithmic_bytes_per_launch': prep_bytes, 'avg_launch_ms': phases['prep_rdm12_ms'], 'peak_source': peak_src}
+    dmma_peak, dmma_src = measure_fp64_peak(timed)
+    rot_flops = 8.0 * n ** 5
+    rot_tf = rot_flops / (phases['rotate_rdm2_ms'] * 1e-3) / 1e12
+    roofline_rotate = {'kernel': 'rotate_tma_kernel x 4 passes (4-index rotation, FP64 DMMA fed by TMA)', 'bound': 'tensor',
+                       'achieved': rot_tf, 'peak': dmma_peak, 'unit': 'TFLOP/s', 'frac': rot_tf / dmma_peak, 'flops_per_launch_set': rot_flops,
+                       'ms': phases['rotate_rdm2_ms'], 'peak_source': dmma_src}
 
     # ---- e2e through the public API from pinned host memory ------------------------------------------------
     e2e = None
@@ -430,30 +569,49 @@ def run_b200_arm(args):
         api_step()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             api_step()      # all-pairs pass + sweep through the API; results come back to the host inside the call
-        e2e_s = (time.perf_counter() - t0) / args.steps
+        e2e_s = (time.perf_counter() - t0) / steps
         h2d = 8 * (n ** 4 + n ** 2) + 8 * n * n + 8 * (len(pairs_np) + P)
-        d2h = LS_DTYPE.itemsize * (len(pairs_np) + P) + 8 * n * n + 32
+        d2h = LS_DTYPE.itemsize * (len(pairs_np) + P) + 8 * n * n + 8 * n * n + 32
         e2e = {'value': evals_per_step / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_s * 1e3,
-               'api': 'qio_b200.qio.prep_rdm12(host dm1, pinned host dm2) -> grad.jacobi.linesearch_pairs -> '
-                      'grad.jacobi.minimize_orb_corr_jacobi(max_cycle=1); rotations, U, records read back'}
+               'api': 'qio_b200.qio.prep_rdm12(host dm1, pinned host dm2) -> grad.jacobi.linesearch_pairs -> mutual_info.mutual_information '
+                      '-> grad.jacobi.minimize_orb_corr_jacobi(max_cycle=1, decision audit on); rotations, U, records, MI matrix read back'}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if detail and not args.no_cpu_baseline:
         cpu = cpu_reference_sample(n)
-        cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample', 'blas_threads')}
 
     out = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': steps, 'warmup': warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic', 'config': workload_config(n, 1), 'clocks': clocks, 'e2e': e2e,
-        'gpu_launches': launches_per_step * args.steps, 'roofline': roofline, 'cpu_baseline': cpu,
+        'gpu_launches': launches_per_step * steps, 'roofline': roofline, 'roofline_prep': roofline_prep,
+        'roofline_rotate': roofline_rotate, 'cpu_baseline': cpu,
         'evals_per_step': evals_per_step, 'rotations_accepted': n_accepted, 'cost_after_cycle': cost_after,
-        'phases': phases,
+        'decision_audit': decision_audit, 'phases': phases, 'peak_memory_gb': peak_mem,
     }
-    print(json.dumps(out))
+    del dm2_d, Gamma, work, dm2_h
+    return out
+
+
+def measure_fp64_peak(timed):
+    """In-run FP64 matrix peak for the rotation's roofline: cuBLAS DGEMM 8192^3 through torch (library call, used as a
+    yardstick only; the hand-written DMMA microbenchmark of profiles/tools/fp64_peak.cu measured 37.1 TFLOP/s)."""
+    import torch
+    try:
+        m = 8192
+        a = torch.randn((m, m), dtype=torch.float64, device='cuda')
+        b = torch.randn((m, m), dtype=torch.float64, device='cuda')
+        torch.matmul(a, b)
+        ms = min(timed(lambda: torch.matmul(a, b), 2) for _ in range(3))
+        tf = 2.0 * m ** 3 / (ms * 1e-3) / 1e12
+        del a, b
+        return tf, f'measured in this run: cuBLAS DGEMM {m}^3 (torch.matmul f64), best of 3 x 2'
+    except Exception as exc:       # noqa: BLE001
+        return 37.1, f'fallback: DMMA m8n8k4 microbenchmark of round 1 (in-run DGEMM failed: {exc})'
 
 
 def sweep_phase_table(tsum, npairs):
@@ -476,14 +634,46 @@ def run_b200_multi(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
+    from qio_b200 import selfcheck
+    from qio_b200.peers import PeerGroup
+
+    sys.stderr.write(f'[bench] rank {rank}: NCCL communicator of {dist.get_world_size()} ranks (torch.distributed, backend nccl)\n')
+    peers = PeerGroup()
+    parity = None
+    if not args.no_parity:
+        # the sharded path against the single-GPU path on the very GPUs of this run, and the mailbox signalling itself
+        par = selfcheck.multi_gpu_parity(peers, sizes=(13, 24))
+        stress = selfcheck.mailbox_stress(peers, iterations=2000)
+        parity = {'ok': bool(par['ok'] and stress['ok']), 'checks': par['checks'], 'failures': par['failures'][:5], 'sizes': par['sizes'],
+                  'mailbox_stress': stress,
+                  'what': 'qio_b200.selfcheck: sharded prep / rotation (all-to-all re-shard) / all-pairs pass / MI matrix / Jacobi cycles / flush vs '
+                          'the single-GPU path on every rank, decisions bitwise identical; then tagged 16-byte stores into every peer mailbox'}
+    out = multi_gpu_leg(args, args.n, args.steps, max(args.warmup, 3), rank, world, local_rank, peers, detail=True)
+    if rank == 0:
+        out['parity_ok'] = None if parity is None else parity['ok']
+        out['parity'] = parity
+        out['comm_nranks'] = world
+    if not args.no_north_star and args.n != NORTH_STAR_N:
+        torch.cuda.empty_cache()
+        ns = multi_gpu_leg(args, NORTH_STAR_N, max(1, min(args.steps, 2)), 3, rank, world, local_rank, peers, detail=False)
+        if rank == 0:
+            out['north_star'] = north_star_record(ns)
+    if rank == 0:
+        print(json.dumps(out))
+    peers.close()
+    dist.destroy_process_group()
+
+
+def multi_gpu_leg(args, n, steps, warmup, rank, world, local_rank, peers, detail):
+    import torch
+    import torch.distributed as dist
+
     from qio_b200 import device as dev
     from qio_b200 import synth, tables
     from qio_b200._lib import LS_DTYPE
     from qio_b200.grad import jacobi as JA
-    from qio_b200.peers import PeerGroup
     from qio_b200.sharded import ShardedRDM, shard_range
 
-    n = args.n
     P = n * (n - 1) // 2
     inact = list(range(n))
     a0, a1 = shard_range(n, rank, world)
@@ -509,29 +699,35 @@ def run_b200_multi(args, rank, world, local_rank):
     inds_d = dev.to_device(np.arange(n, dtype=np.int32), dev.I32)
     tabs = tables.device_tables()
     fine_len = tabs.host['fine_len']
-    peers = PeerGroup()
     W = dev.empty(n, n)
-    work_full = dev.empty(n, n, n, n)
     state = {}
+    torch.cuda.reset_peak_memory_stats()
+    mem_before = torch.cuda.memory_allocated()
 
     def step(dm1_in, dm2_in):
         st = ShardedRDM.from_solver(dm1_in, dm2_in, n, peers=peers)
-        st.rotate_(U0_d, work_full)
+        st.rotate_(U0_d)
         dX, ddX, rec_all = st.all_pairs_pass(inact, tabs)
+        mi = st.mutual_information()
         Ud = U0_d.clone()
         dev.sweep_reset(W, n)
-        rec, n_acc, cost, flags = st.sweep_cycle(Ud, W, pairs_np, mask, inds_d, tabs)
-        st.flush(W, work_full)
-        state.update(rec_all=rec_all, rec=rec, n_acc=n_acc, cost=cost, U=Ud, st=st)
+        rec, n_acc, cost, flags = st.sweep_cycle(Ud, W, pairs_np, mask, inds_d, tabs)      # includes the decision audit
+        st.flush(W)
+        state.update(rec_all=rec_all, rec=rec, n_acc=n_acc, cost=cost, U=Ud, st=st, mi=mi, audit=st.last_audit)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step(dm1_d, dm2_d)
     torch.cuda.synchronize()
+    peak_mem = (torch.cuda.max_memory_allocated() - mem_before) / 1e9
     ra = state['rec_all'].cpu().numpy().view(LS_DTYPE)
     rs = state['rec']
     rows_a = np.where(ra['coarse_index'] >= 0, ra['coarse_index'], 0)
     rows_s = np.where(rs['coarse_index'] >= 0, rs['coarse_index'], 0)
     evals_per_step = int((1 + 314 + fine_len[rows_a]).sum() + (1 + 314 + fine_len[rows_s]).sum())
+    audit = state['audit']
+    decision_audit = {'pairs': audit['pairs'], 'mismatches': len(audit['mismatches']), 'near_ties_below_1e-12': len(audit['near_ties']),
+                      'unexplained': len(audit['unexplained']), 'min_fine_margin': audit['min_fine_margin'],
+                      'min_coarse_margin': audit['min_coarse_margin']}
 
     def timed_steps(dm1_in, dm2_in, k):
         sampler = ClockSampler(local_rank)
@@ -550,64 +746,80 @@ def run_b200_multi(args, rank, world, local_rank):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / k, sampler.stop()
 
-    ms_per_step, clocks = timed_steps(dm1_d, dm2_d, args.steps)
+    ms_per_step, clocks = timed_steps(dm1_d, dm2_d, steps)
     value = evals_per_step / (ms_per_step * 1e-3)
     e2e = None
     if not args.no_e2e:
         step(dm1_h, dm2_h)
-        e2e_ms, _ = timed_steps(dm1_h, dm2_h, args.steps)
+        e2e_ms, _ = timed_steps(dm1_h, dm2_h, steps)
         e2e = {'value': evals_per_step / (e2e_ms * 1e-3), 'unit': UNIT,
                'h2d_bytes_per_step': int(8 * (n ** 4 + n ** 2) + 8 * (len(pairs_np) + P)),
                'd2h_bytes_per_step': int(LS_DTYPE.itemsize * (len(pairs_np) + P) + 64 * world), 'ms_per_step': e2e_ms,
                'api': 'qio_b200.sharded.ShardedRDM.from_solver(host dm1, pinned host dm2 shard) -> rotate_ -> all_pairs_pass '
-                      '-> sweep_cycle -> flush on every rank; records read back'}
+                      '-> mutual_information -> sweep_cycle (decision audit on) -> flush on every rank; records read back'}
 
-    # the sweep kernel alone (dominant kernel), from the step's own start state
-    st = ShardedRDM.from_solver(dm1_d, dm2_d, n, peers=peers)
-    st.rotate_(U0_d, work_full)
+    # ---- phases: the sweep kernel alone (dominant kernel) and what surrounds it, from the step's own start state -----------
+    def tmax(fn):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), r
+
+    phases = {}
+    phases['prep_upload_ms'], st = tmax(lambda: ShardedRDM.from_solver(dm1_d, dm2_d, n, peers=peers))
+    phases['rotate_sharded_ms'], _ = tmax(lambda: st.rotate_(U0_d))
+    phases['all_pairs_pass_ms'], _ = tmax(lambda: st.all_pairs_pass(inact, tabs))
+    phases['mutual_information_ms'], _ = tmax(lambda: st.mutual_information())
     Ud = U0_d.clone()
     dev.sweep_reset(W, n)
     pairs_d = dev.to_device(pairs_np, dev.I32)
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    _, summ = dev.sweep_cycle(st.gamma, st.G, Ud, W, n, pairs_d, mask, tabs, st.a0, st.na, peers)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    sweep_ms = float(t.item())
+    sweep_ms, (_, summ) = tmax(lambda: dev.sweep_cycle(st.gamma, st.G, Ud, W, n, pairs_d, mask, tabs, st.a0, st.na, peers))
     n_acc = int(dev.to_host(summ)[0])
-    os.environ['QIO_B200_SWEEP_TIMERS'] = '1'       # one more cycle with the timed build, for the phase table only
-    tsum = dev.to_host(dev.sweep_cycle(st.gamma, st.G, Ud, W, n, pairs_d, mask, tabs, st.a0, st.na, peers)[1])
-    os.environ.pop('QIO_B200_SWEEP_TIMERS', None)
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    peak = json.load(open(peaks_path))['hbm_gbs'] if os.path.exists(peaks_path) else 6650.0
+    phases['jacobi_cycle_kernel_ms'] = sweep_ms
+    phases['flush_sharded_ms'], _ = tmax(lambda: st.flush(W))
+    phases['step_minus_sweep_kernel_ms'] = ms_per_step - sweep_ms
+    if detail:
+        tsum = dev.to_host(dev.sweep_cycle(st.gamma, st.G, Ud, W, n, pairs_d, mask, tabs, st.a0, st.na, peers, timers=True)[1])
+        phases['sweep_phase_us_per_pair'] = sweep_phase_table(tsum, len(pairs_np))
+    peak, peak_src = hbm_peak()
+    acc_mask = rs['accepted'] != 0
     algo_bytes = 16.0 * (n ** 4 - (n - 2) ** 4) * n_acc / world
+    moved = moved_bytes(n, na, pairs_np, acc_mask)
     achieved = algo_bytes / (sweep_ms * 1e-3) / 1e9
     engine = dev.sweep_engine(n, na)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'sweep_traffic.json')
+    if os.path.exists(tpath):
+        ent = json.load(open(tpath)).get(f'engine{engine}', {}).get(f'{n}x{world}')
+        if ent:
+            traffic = ent['dram_bytes_per_accepted_rotation'] * n_acc
+            traffic_src = f"{ent['source']} (per rank)"
     roofline = {'kernel': ('sweep3_kernel (pipelined persistent Jacobi cycle)' if engine == 3 else 'sweep_kernel (persistent Jacobi cycle, grid barrier per pair)') + ', per GPU', 'bound': 'hbm', 'achieved': achieved,
-                'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
                 'algorithmic_bytes_per_launch': algo_bytes, 'avg_launch_ms': sweep_ms, 'launches_timed': 1,
-                'kernel_min_bytes_per_launch': (64.0 * n ** 3 * n_acc + 32.0 * n * n * len(pairs_np)) / world,
-                'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if os.path.exists(peaks_path) else 'fallback',
+                'moved_bytes_per_launch': moved, 'frac_moved': moved / (sweep_ms * 1e-3) / 1e9 / peak,
+                'frac_dram': (traffic / (sweep_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                'peak_source': peak_src,
                 'note': 'per-GPU share of the algorithmic bytes (16 (n^4-(n-2)^4) per accepted rotation / n_gpus) over the '
-                        'slowest rank\'s kernel time'}
-    if rank == 0:
-        out = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(n, world),
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': (2 + 1 + 3 * na + 1 + 1 + 2 + 5 + 3) * args.steps,
-            'roofline': roofline, 'cpu_baseline': None, 'evals_per_step': evals_per_step,
-            'rotations_accepted': n_acc, 'cost_after_cycle': state['cost'],
-            'phases': {'jacobi_cycle_kernel_ms': sweep_ms,
-                       'sweep_phase_us_per_pair': sweep_phase_table(tsum, len(pairs_np))},
-        }
-        print(json.dumps(out))
-    peers.close()
-    dist.destroy_process_group()
+                        'slowest rank\'s kernel time; frac_moved = bytes this rank\'s shard really reads + writes / time / peak'}
+    out = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
+        'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(n, world),
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': count_launches(engine, world) * steps,
+        'roofline': roofline, 'cpu_baseline': None, 'evals_per_step': evals_per_step,
+        'rotations_accepted': n_acc, 'cost_after_cycle': state['cost'], 'decision_audit': decision_audit,
+        'phases': phases, 'peak_memory_gb': peak_mem,
+    }
+    del dm2_d, dm2_h, st
+    state.clear()
+    return out
 
 
 def main():
