@@ -307,10 +307,10 @@ def count_launches(engine, world=1, audit=True):
 
 
 def run_b200_arm(args):
-    # NCCL's own log (communicator sizes, transports) goes to stderr, never to stdout: rank 0 prints one JSON line only
-    os.environ.setdefault('NCCL_DEBUG', 'INFO')
-    os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+    # NCCL prints its version banner (and, at INFO, its whole log) on STDOUT: default to WARN so that rank 0's JSON line is
+    # the only thing there; a caller who exports NCCL_DEBUG keeps it.  The communicator size is reported by the bench itself
+    # (stderr line per rank + "comm_nranks" in the JSON line), and the JSON line is printed last, after the group is destroyed.
+    os.environ.setdefault('NCCL_DEBUG', 'WARN')
     import torch
     import torch.distributed as dist
 
@@ -658,10 +658,11 @@ def run_b200_multi(args, rank, world, local_rank):
         ns = multi_gpu_leg(args, NORTH_STAR_N, max(1, min(args.steps, 2)), 3, rank, world, local_rank, peers, detail=False)
         if rank == 0:
             out['north_star'] = north_star_record(ns)
-    if rank == 0:
-        print(json.dumps(out))
     peers.close()
     dist.destroy_process_group()
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(out), flush=True)
 
 
 def multi_gpu_leg(args, n, steps, warmup, rank, world, local_rank, peers, detail):

@@ -57,6 +57,9 @@ typedef struct qio_b200_ls_result {
     double cost0;         /* pair cost at theta = 0                                          */
     double coarse_margin; /* min(|cost0 - best|, second best - best) on the coarse grid      */
     double fine_margin;   /* min over the fine scan of |cost - (new_cost + 1e-8)|            */
+                          /* (both margins are +inf in the records of the pipelined sweep    */
+                          /* kernel: they are off its per-pair critical path and come from   */
+                          /* the strict-order audit pass over qio_b200_sweep_options.blocks_out) */
     double cos_theta;     /* cos / sin of the accepted angle (1, 0 when not accepted)        */
     double sin_theta;
     double reserved;

@@ -48,8 +48,7 @@ struct LineSearchSmemT {
     double2 fine_cs[LS_MAX_FINE];     // cos, sin of each fine angle
     int scan_last;                    // results of warp 0's accept scan
     double scan_cur;
-    unsigned accw[LS_MAX_FINE / 32];  // bit k: entry k was accepted by the scan
-    double wmargin[LS_MAX_FINE / 32];
+    double scan_margin;               // smallest |cost - (new_cost + 1e-8)| over every comparison of the scan
     MinIdx warp_best[NT / 32];
     MinIdx best;
     double cost0;
@@ -87,7 +86,12 @@ struct NoDecisionHook {
 
 // `decided(accepted, cos, sin)` is called by thread 0 as soon as the angle is known (before the margins are taken): the
 // pipelined sweep publishes the angle there.
-template <int NT, typename Block, typename Hook = NoDecisionHook>
+// FINAL_SYNC = false leaves out the closing barrier: the caller then must not touch `sm` before its own next barrier of
+// the same NT threads (the pipelined sweep's block contraction provides two).
+// MARGINS = false skips the two diagnostic margins (reported as +inf): the pipelined sweep keeps them off its per-pair
+// critical path -- the decision audit re-derives every decision, margins included, from the pair blocks in one batched
+// launch afterwards.
+template <int NT, typename Block, typename Hook = NoDecisionHook, bool FINAL_SYNC = true, bool MARGINS = true>
 __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool j_in, const ThetaTablesDev &tab,
                                                  LineSearchSmemT<NT> &sm, qio_b200_ls_result &res, Hook decided = Hook()) {
     static_assert(NT >= LS_MAX_FINE && NT % 32 == 0, "line search needs at least 256 threads");
@@ -124,16 +128,16 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
         }
     }
     LS_PROF(0)
-    mine = warp_min(mine);
+    mine = warp_min<MARGINS>(mine);
     if (lane == 0) sm.warp_best[warp] = mine;
     ls_sync<NT>();
     MinIdx best = (lane < NT / 32) ? sm.warp_best[lane] : MinIdx{INFINITY, 0x7fffffff, INFINITY};
-    best = warp_min(best);              // every warp reduces the NT/32 partial results redundantly: no second barrier
+    best = warp_min<MARGINS>(best);     // every warp reduces the NT/32 partial results redundantly: no second barrier
     const double cost0 = sm.cost0;
     const bool improved = cost0 > best.v;
     const int row = improved ? best.idx : 0;
     const double start = improved ? best.v : cost0;
-    const double coarse_margin = fmin(fabs(cost0 - best.v), best.v2 - best.v);
+    const double coarse_margin = MARGINS ? fmin(fabs(cost0 - best.v), best.v2 - best.v) : INFINITY;
     LS_PROF(1)
 
     // ---- fine grid of that coarse point ---------------------------------------------------
@@ -157,20 +161,25 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
     LS_PROF(2)
 
     // ---- the accept scan, by warp 0 alone (lane l holds the entries l, l + 32, ...): no CTA-wide barrier inside the
-    // rounds, one warp-wide integer minimum per round ----------------------------------------------------------------
+    // rounds, one warp-wide integer minimum per round.  The margin -- the smallest |cost - (new_cost + 1e-8)| over every
+    // comparison the reference's sequential scan makes -- is collected on the way: entries between the last accepted one and
+    // the next accepted one were compared against the running cost, the entries of a run of consecutive accepts each
+    // against its predecessor. ------------------------------------------------------------------------------------------
     if (warp == 0) {
-        double thr[NW];
-        unsigned am[NW], accw[NW];
+        double thr[NW], dprev[NW];
+        unsigned am[NW];
 #pragma unroll
         for (int j = 0; j < NW; ++j) {
             const int k = lane + 32 * j;
             thr[j] = sm.fine_thr[k];
-            const bool a = k > 0 && k < L && sm.fine_val[k > 0 ? k - 1 : 0] > thr[j];     // cost_{k-1} > cost_k + 1e-8
+            const double pv = sm.fine_val[k > 0 ? k - 1 : 0];
+            const bool a = k > 0 && k < L && pv > thr[j];     // cost_{k-1} > cost_k + 1e-8
             am[j] = __ballot_sync(0xffffffffu, a);
-            accw[j] = 0u;
+            dprev[j] = fabs(pv - thr[j]);
         }
         int last = -1;          // last accepted index (uniform)
         double cur = start;     // running cost (uniform)
+        double mg = INFINITY;
         for (;;) {
             // first k beyond `last` with cost_k + 1e-8 < cost (k < L implied: thr = +inf beyond)
             int mine = 0x7fffffff;
@@ -178,6 +187,15 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
             for (int j = NW - 1; j >= 0; --j)
                 if (lane + 32 * j > last && thr[j] < cur) mine = lane + 32 * j;
             const int first = (int)__reduce_min_sync(0xffffffffu, (unsigned)mine);
+            // every entry in (last, first] (to the end of the grid if nothing is accepted any more) met the running cost
+            if (MARGINS) {
+                const int upto = first == 0x7fffffff ? L - 1 : first;
+#pragma unroll
+                for (int j = 0; j < NW; ++j) {
+                    const int k = lane + 32 * j;
+                    if (k > last && k <= upto) mg = fmin(mg, fabs(cur - thr[j]));
+                }
+            }
             if (first == 0x7fffffff) break;
             // extend over the run of consecutive accepts that follows: first zero bit of the mask above `first`
             // (bits at and beyond L are zero by construction, so the run always ends before L)
@@ -196,46 +214,29 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
                 }
                 if (w < NW) e = w * 32 + __ffs(zeros) - 2;                       // last set bit before the first zero
             }
+            if (MARGINS) {
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {                                   // record the accepted run [first, e]
-                const int lo = max(first, w * 32), hi = min(e, w * 32 + 31);
-                if (lo <= hi) accw[w] |= (hi - lo == 31 ? ~0u : ((1u << (hi - lo + 1)) - 1u) << (lo - w * 32));
+                for (int j = 0; j < NW; ++j) {                               // the run (first, e]: each against its predecessor
+                    const int k = lane + 32 * j;
+                    if (k > first && k <= e) mg = fmin(mg, dprev[j]);
+                }
             }
             last = e;
             cur = sm.fine_val[e];
         }
+        // the angle is known: thread 0 hands it to the caller before anybody waits at the barrier below
+        if (lane == 0) decided(last >= 0, last >= 0 ? sm.fine_cs[last].x : 1.0, last >= 0 ? sm.fine_cs[last].y : 0.0);
+        if (MARGINS) mg = warp_min_double(mg);
         if (lane == 0) {
             sm.scan_last = last;
             sm.scan_cur = cur;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) sm.accw[w] = accw[w];
+            sm.scan_margin = mg;
         }
     }
     ls_sync<NT>();
     const int last = sm.scan_last;
-    const double cur = sm.scan_cur;
-    if (tid == 0) decided(last >= 0, last >= 0 ? sm.fine_cs[last].x : 1.0, last >= 0 ? sm.fine_cs[last].y : 0.0);
+    const double cur = sm.scan_cur, margin = sm.scan_margin;
     LS_PROF(3)
-
-    // ---- smallest |cost - (new_cost + 1e-8)| over every comparison of the reference's scan: entry k was compared
-    // against the cost of the last accepted entry before k (or the starting cost); one entry per thread -----------
-    if (tid < LS_MAX_FINE) {
-        double mg = INFINITY;
-        if (tid < L) {
-            int prev = -1;
-            unsigned m = sm.accw[warp] & ((lane == 0) ? 0u : (~0u >> (32 - lane)));      // bits below this entry
-            int w = warp;
-            while (!m && w > 0) m = sm.accw[--w];
-            if (m) prev = w * 32 + 31 - __clz(m);
-            mg = fabs((prev >= 0 ? sm.fine_val[prev] : start) - my_thr);
-        }
-        mg = warp_min_double(mg);
-        if (lane == 0) sm.wmargin[warp] = mg;
-    }
-    ls_sync<NT>();
-    double margin = INFINITY;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) margin = fmin(margin, sm.wmargin[w]);
     LS_PROF(4)
     const int fidx = last;
     res.coarse_index = improved ? best.idx : -1;
@@ -257,7 +258,7 @@ __device__ __forceinline__ void cta_linesearch_t(const Block &b, bool i_in, bool
     }
     res.reserved = 0.0;
     LS_PROF(5)
-    ls_sync<NT>();   // smem may be reused by the caller
+    if (FINAL_SYNC) ls_sync<NT>();   // smem may be reused by the caller
 }
 
 __device__ __forceinline__ void cta_linesearch(const PairBlock &b, bool i_in, bool j_in, const ThetaTablesDev &tab,

@@ -357,12 +357,14 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k)
 }
 
 // Same result as a merge() tree over the lanes: first index of the minimum, second best value among the OTHER indices.
+// SECOND = false leaves the second-best value out (+inf): two hardware reductions fewer.
+template <bool SECOND = true>
 __device__ __forceinline__ MinIdx warp_min(MinIdx x) {
     const unsigned long long key = dkey(x.v), kmin = warp_min_u64(key);
     MinIdx r;
     r.v = dunkey(kmin);
     r.idx = (int)__reduce_min_sync(0xffffffffu, key == kmin ? (unsigned)x.idx : 0x7fffffffu);
-    r.v2 = dunkey(warp_min_u64(dkey(x.idx == r.idx ? x.v2 : x.v)));
+    r.v2 = SECOND ? dunkey(warp_min_u64(dkey(x.idx == r.idx ? x.v2 : x.v))) : INFINITY;
     return r;
 }
 

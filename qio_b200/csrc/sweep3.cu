@@ -1055,24 +1055,36 @@ __device__ __forceinline__ void aux_main(const Params &p, int *flag_sm, double *
 // =====================================================================================================================
 // CTA 0: prefetch (warps 10..15) and search (warps 0..9)
 // =====================================================================================================================
+constexpr int MAXY = 4;                              // orbitals of pairs k-1 and k: what is left after the fetch warps' contraction
+constexpr int SBP_WORDS = MAXY * MAXY * MAXY * MAXY + 2 * MAXY * MAXY;   // reduced super block + its gamma part
+constexpr int Z_WORDS = MAXM * MAXM * MAXM * MAXY;   // largest intermediate of the fetch warps' contraction
+
 struct SearchSmem {
     LineSearchSmemT<SEARCH_THREADS> ls;
-    double sb[2][TOT_WORDS];        // double-buffered super block (+ gamma part) of the pair being / to be searched
+    double sb[TOT_WORDS];           // super block (+ gamma part) being fetched; consumed by the fetch warps themselves
+    double z[2][Z_WORDS];           // their contraction scratch (ping-pong)
+    double sbp[2][SBP_WORDS];       // double-buffered REDUCED super block of the pair being / to be searched: rotation k-2 applied,
+                                    // restricted to the <= 4 orbitals Y of pairs k-1 and k: [y1][y2][y3][y4] (stride 4), then gamma [spin][y][y']
     int sb_ok[2];
-    double y1[2 * MAXM * MAXM * MAXM];   // contraction scratch
-    double y2[4 * MAXM * MAXM];
-    double y3[8 * MAXM];
     double blk[QIO_B200_BLOCK_DOUBLES];
-    double T[2 * MAXM];
     PairCoef pc;
     double2 coarse_cs[320];
     int32_t fine_len[320];
-    int meta[2][12];                // per buffer: m, pos(i), pos(j), inactive(i), inactive(j), pa0, pb0, pa1, pb1 (-1: none)
+    int meta[2][8];                 // per buffer: Y index of i_k, of j_k, inactive(i), inactive(j), Y index of i_{k-1}, j_{k-1} (-1: no such pair)
+    // angle history for the fetch warps: written by search thread 0 the moment pair k is decided
+    int hist_acc[4];
+    double hist_c[4], hist_s[4];
+    int decided;                    // last decided pair (-1 at start); volatile accesses
     int fetch_abort;
 };
 
 // named barriers: 1 = line search (320), 2 + b = full[b], 4 + b = empty[b] (512: one side arrives, the other syncs),
 // 6 = prefetch warps among themselves (192)
+// The prefetch warps: gather super block k (the workers' / ranks' totals), then take the FIRST of the two pending rotations
+// (pair k-2, known since the end of search k-2) off the search threads' critical path:
+//     P'[y1,y2,y3,y4] = sum_{pqrs} G0[Y_1,p] G0[Y_2,q] G0[Y_3,r] G0[Y_4,s] P_k[p,q,r,s],   Y = orbitals of pairs k-1 and k (<= 4),
+// G0 = rotation k-2 in the orbitals D_k (rows of i_{k-2}, j_{k-2} have two non-zeros, every other row is a unit vector), as four
+// single-index passes; likewise for the gamma part.  The search threads are left with rotation k-1 on <= 4^4 numbers.
 __device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
     const int ft = threadIdx.x - SEARCH_THREADS;
     for (int k = 0; k < p.P; ++k) {
@@ -1081,10 +1093,7 @@ __device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
         const int32_t *dt = p.dtab + (size_t)k * DT_STRIDE;
         const int m_k = dt[0];
         const int ne = m_k * m_k * m_k * m_k, ng = 2 * m_k * m_k;
-        if (ft < 9) {       // meta: m, pos(i), pos(j), inactive(i), inactive(j), pa0, pb0, pa1, pb1
-            const int src = ft == 0 ? 0 : (ft <= 2 ? 6 + ft : (ft <= 4 ? 10 + ft : 4 + ft));
-            sm.meta[b][ft] = dt[src];
-        }
+        const int pos_i = dt[7], pos_j = dt[8], pa0 = dt[9], pb0 = dt[10], pa1 = dt[11], pb1 = dt[12];
         bool ok = true;
         for (int e = ft; e < ne + ng; e += FETCH_THREADS) {
             const bool is_g = e >= ne;
@@ -1114,10 +1123,100 @@ __device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
                 ok &= spin_until(p, [&]() { return ll_load(w, v, (unsigned)(k + 1)); });
                 acc = __longlong_as_double((long long)v);
             }
-            sm.sb[b][word] = acc;
+            sm.sb[word] = acc;
+        }
+        // rotation k-2 (identity if that pair does not exist or was not accepted)
+        int acc0 = 0;
+        double c0 = 1.0, s0 = 0.0;
+        if (k >= 2 && ok) {
+            ok &= spin_until(p, [&]() { return *reinterpret_cast<volatile int *>(&sm.decided) >= k - 2; });
+            acc0 = sm.hist_acc[(k - 2) & 3];
+            c0 = sm.hist_c[(k - 2) & 3];
+            s0 = sm.hist_s[(k - 2) & 3];
         }
         if (!ok) sm.fetch_abort = 1;
         if (k == 0 && ft == 0 && ok) atomicExch(p.abort_flag + 1, 1u);      // start-up is over: the normal time-out applies
+        named_sync<6, FETCH_THREADS>();
+        if (!sm.fetch_abort) {
+            // Y: the orbitals of pairs k-1 and k, as positions in D_k, in order of first appearance
+            // (kept in scalars and selected with compares: a runtime-indexed array would live in local memory)
+            int Y0 = -1, Y1 = -1, Y2 = -1, Y3 = -1, nY = 0;
+            auto add = [&](int cand) {
+                if (cand < 0 || cand == Y0 || cand == Y1 || cand == Y2 || cand == Y3) return;
+                if (nY == 0) Y0 = cand;
+                else if (nY == 1) Y1 = cand;
+                else if (nY == 2) Y2 = cand;
+                else Y3 = cand;
+                ++nY;
+            };
+            add(pa1);
+            add(pb1);
+            add(pos_i);
+            add(pos_j);
+            auto yidx = [&](int pos) { return pos == Y0 ? 0 : (pos == Y1 ? 1 : (pos == Y2 ? 2 : (pos == Y3 ? 3 : -1))); };
+            // row Y[y] of G0: cA e_pA + cB e_pB
+            auto g0row = [&](int y, int &pA, double &cA, int &pB, double &cB) {
+                const int pos = y == 0 ? Y0 : (y == 1 ? Y1 : (y == 2 ? Y2 : Y3));
+                if (acc0 && pa0 >= 0 && pos == pa0) { pA = pa0; cA = c0; pB = pb0; cB = s0; }
+                else if (acc0 && pa0 >= 0 && pos == pb0) { pA = pa0; cA = -s0; pB = pb0; cB = c0; }
+                else { pA = pos; cA = 1.0; pB = pos; cB = 0.0; }
+            };
+            const int m = m_k, n1 = nY, n2 = nY * nY, n3 = n2 * nY;
+            // pass 1 (index s): z0[pqr][y4]; the gamma part alongside: sbp[256 + spin*16 + y*4 + y']
+            for (int o = ft; o < m * m * m * n1; o += FETCH_THREADS) {
+                const int pqr = o / n1, y4 = o - pqr * n1;
+                int pA, pB;
+                double cA, cB;
+                g0row(y4, pA, cA, pB, cB);
+                sm.z[0][o] = cA * sm.sb[pqr * m + pA] + cB * sm.sb[pqr * m + pB];
+            }
+            for (int o = ft; o < 2 * n2; o += FETCH_THREADS) {
+                const int spin = o / n2, r = o - spin * n2, y = r / n1, yy = r - y * n1;
+                int pA, pB, qA, qB;
+                double cA, cB, dA, dB;
+                g0row(y, pA, cA, pB, cB);
+                g0row(yy, qA, dA, qB, dB);
+                const double *gm = sm.sb + SB_MAX + spin * m * m;
+                sm.sbp[b][MAXY * MAXY * MAXY * MAXY + spin * MAXY * MAXY + y * MAXY + yy] =
+                    cA * (dA * gm[pA * m + qA] + dB * gm[pA * m + qB]) + cB * (dA * gm[pB * m + qA] + dB * gm[pB * m + qB]);
+            }
+            named_sync<6, FETCH_THREADS>();
+            // pass 2 (index r): z1[pq][y3][y4]
+            for (int o = ft; o < m * m * n2; o += FETCH_THREADS) {
+                const int pq = o / n2, r = o - pq * n2, y3 = r / n1, y4 = r - y3 * n1;
+                int pA, pB;
+                double cA, cB;
+                g0row(y3, pA, cA, pB, cB);
+                sm.z[1][o] = cA * sm.z[0][(pq * m + pA) * n1 + y4] + cB * sm.z[0][(pq * m + pB) * n1 + y4];
+            }
+            named_sync<6, FETCH_THREADS>();
+            // pass 3 (index q): z0[p][y2][y3 y4]
+            for (int o = ft; o < m * n3; o += FETCH_THREADS) {
+                const int pp = o / n3, r = o - pp * n3, y2 = r / n2, rest = r - y2 * n2;
+                int pA, pB;
+                double cA, cB;
+                g0row(y2, pA, cA, pB, cB);
+                sm.z[0][o] = cA * sm.z[1][(pp * m + pA) * n2 + rest] + cB * sm.z[1][(pp * m + pB) * n2 + rest];
+            }
+            named_sync<6, FETCH_THREADS>();
+            // pass 4 (index p): sbp[y1][y2][y3][y4] with stride MAXY
+            for (int o = ft; o < n1 * n3; o += FETCH_THREADS) {
+                const int y1 = o / n3, r = o - y1 * n3, y2 = r / n2, r2 = r - y2 * n2, y3 = r2 / n1, y4 = r2 - y3 * n1;
+                int pA, pB;
+                double cA, cB;
+                g0row(y1, pA, cA, pB, cB);
+                sm.sbp[b][((y1 * MAXY + y2) * MAXY + y3) * MAXY + y4] = cA * sm.z[0][pA * n3 + r] + cB * sm.z[0][pB * n3 + r];
+            }
+            if (ft == 0) {
+                int *mt = sm.meta[b];
+                mt[0] = yidx(pos_i);
+                mt[1] = yidx(pos_j);
+                mt[2] = dt[13];
+                mt[3] = dt[14];
+                mt[4] = pa1 >= 0 ? yidx(pa1) : -1;
+                mt[5] = pb1 >= 0 ? yidx(pb1) : -1;
+            }
+        }
         named_sync<6, FETCH_THREADS>();
         if (ft == 0) sm.sb_ok[b] = sm.fetch_abort ? 0 : 1;
         __threadfence_block();
@@ -1160,64 +1259,46 @@ __device__ __forceinline__ void search_main(const Params &p, SearchSmem &sm) {
             tq = t;
         }
         const int *mt = sm.meta[b];
-        const bool i_in = mt[3] != 0, j_in = mt[4] != 0;
-        if (tid < 2 * MAXM) {
-            // T[target][col] = (G1 G0)[x, col]: the target orbital x (i or j of pair k) after the pending rotations
-            // G0 (pair k-2) and G1 (pair k-1), in terms of the orbitals D before them.  G(v)[y, col] has <= 2 non-zeros.
-            const int tg = tid / MAXM, col = tid - tg * MAXM, x = mt[1 + tg];
-            auto G = [&](int h, int y, int cc) -> double {      // entry (y, cc) of rotation h (identity if not accepted)
-                const int pa = mt[5 + 2 * h], pb = mt[6 + 2 * h];
-                if (!h_acc[h] || pa < 0) return y == cc ? 1.0 : 0.0;
-                if (y == pa) return cc == pa ? h_c[h] : (cc == pb ? h_s[h] : 0.0);
-                if (y == pb) return cc == pa ? -h_s[h] : (cc == pb ? h_c[h] : 0.0);
-                return y == cc ? 1.0 : 0.0;
-            };
-            double val = 0.0;
-            if (col < mt[0]) {
-                const int pa1 = mt[7], pb1 = mt[8];
-                if (h_acc[1] && pa1 >= 0 && (x == pa1 || x == pb1)) val = G(1, x, pa1) * G(0, pa1, col) + G(1, x, pb1) * G(0, pb1, col);
-                else val = G(0, x, col);
-            }
-            sm.T[tid] = val;
-        }
-        const int m_k = mt[0];
-        ls_sync<SEARCH_THREADS>();
-        {   // B = T^(x4) P_k: contract s, r, q, p in turn
-            const int m = m_k, m2 = m * m, m3 = m2 * m;
-            const double *sb = sm.sb[b], *T = sm.T;
-            for (int o = tid; o < 2 * m3; o += SEARCH_THREADS) {           // y1[pqr][de]
-                const int de = o & 1, pqr = o >> 1;
+        const bool i_in = mt[2] != 0, j_in = mt[3] != 0;
+        {   // B = G1^(x4) P': the pending rotation k-1 on the reduced super block.  Target orbital t (0: i_k, 1: j_k) is the
+            // combination cf[t][0] Y[yy[t][0]] + cf[t][1] Y[yy[t][1]] of the orbitals before rotation k-1.
+            if (tid < QIO_B200_BLOCK_DOUBLES) {
+                const int ya1 = mt[4], yb1 = mt[5];
+                const bool r1 = h_acc[1] && ya1 >= 0;
+                // coefficients / Y indices of target 0 (i_k) and 1 (j_k); selected with compares, never indexed at run time
+                double c00, c01, c10, c11;
+                int y00, y01, y10, y11;
+                auto target = [&](int yx, double &cA, int &yA, double &cB, int &yB) {
+                    if (r1 && yx == ya1) { cA = h_c[1]; yA = ya1; cB = h_s[1]; yB = yb1; }
+                    else if (r1 && yx == yb1) { cA = -h_s[1]; yA = ya1; cB = h_c[1]; yB = yb1; }
+                    else { cA = 1.0; yA = yx; cB = 0.0; yB = yx; }
+                };
+                target(mt[0], c00, y00, c01, y01);
+                target(mt[1], c10, y10, c11, y11);
+                auto cf = [&](int t, int a) { return t ? (a ? c11 : c10) : (a ? c01 : c00); };
+                auto yy = [&](int t, int a) { return t ? (a ? y11 : y10) : (a ? y01 : y00); };
+                const double *sp = sm.sbp[b];
                 double acc = 0.0;
-                for (int s = 0; s < m; ++s) acc += T[de * MAXM + s] * sb[pqr * m + s];
-                sm.y1[o] = acc;
-            }
-            // gamma entries: spin, al, be
-            if (tid >= SEARCH_THREADS - 8) {
-                const int u = tid - (SEARCH_THREADS - 8), spin = u >> 2, al = (u >> 1) & 1, be = u & 1;
-                double acc = 0.0;
-                for (int a = 0; a < m; ++a)
-                    for (int c2 = 0; c2 < m; ++c2) acc += T[al * MAXM + a] * T[be * MAXM + c2] * sb[SB_MAX + spin * m2 + a * m + c2];
-                sm.blk[16 + u] = acc;
-            }
-            ls_sync<SEARCH_THREADS>();
-            for (int o = tid; o < 4 * m2; o += SEARCH_THREADS) {           // y2[pq][ga][de]
-                const int de = o & 1, ga = (o >> 1) & 1, pq = o >> 2;
-                double acc = 0.0;
-                for (int r = 0; r < m; ++r) acc += T[ga * MAXM + r] * sm.y1[(pq * m + r) * 2 + de];
-                sm.y2[o] = acc;
-            }
-            ls_sync<SEARCH_THREADS>();
-            for (int o = tid; o < 8 * m; o += SEARCH_THREADS) {            // y3[p][be][ga][de]
-                const int gd = o & 3, be = (o >> 2) & 1, pp = o >> 3;
-                double acc = 0.0;
-                for (int q = 0; q < m; ++q) acc += T[be * MAXM + q] * sm.y2[(pp * m + q) * 4 + gd];
-                sm.y3[o] = acc;
-            }
-            ls_sync<SEARCH_THREADS>();
-            if (tid < 16) {
-                const int rest = tid & 7, al = tid >> 3;
-                double acc = 0.0;
-                for (int pp = 0; pp < m; ++pp) acc += T[al * MAXM + pp] * sm.y3[pp * 8 + rest];
+                if (tid < 16) {
+                    const int al = tid >> 3, be = (tid >> 2) & 1, ga = (tid >> 1) & 1, de = tid & 1;
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+#pragma unroll
+                            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                                for (int d = 0; d < 2; ++d)
+                                    acc += ((cf(al, a) * cf(be, q)) * (cf(ga, r) * cf(de, d))) *
+                                           sp[((yy(al, a) * MAXY + yy(be, q)) * MAXY + yy(ga, r)) * MAXY + yy(de, d)];
+                } else {
+                    const int u = tid - 16, spin = u >> 2, al = (u >> 1) & 1, be = u & 1;
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+                            acc += (cf(al, a) * cf(be, q)) * sp[MAXY * MAXY * MAXY * MAXY + spin * MAXY * MAXY + yy(al, a) * MAXY + yy(be, q)];
+                }
                 sm.blk[tid] = acc;
             }
             ls_sync<SEARCH_THREADS>();
@@ -1238,12 +1319,17 @@ __device__ __forceinline__ void search_main(const Params &p, SearchSmem &sm) {
         qio_b200_ls_result res;
         // the angle record is published by thread 0 the moment the scan has decided (before the margins are taken)
         auto publish = [&](bool accepted, double cth, double sth) {
+            sm.hist_acc[k & 3] = accepted ? 1 : 0;          // for the prefetch warps (rotation k is their G0 of pair k + 2)
+            sm.hist_c[k & 3] = cth;
+            sm.hist_s[k & 3] = sth;
+            __threadfence_block();
+            *reinterpret_cast<volatile int *>(&sm.decided) = k;
             unsigned long long *w = p.ring + (size_t)(k & (RING - 1)) * 4;
             const unsigned tag = 2u * (unsigned)(k + 1) + (accepted ? 1u : 0u);
             ll_store(w, (unsigned long long)__double_as_longlong(cth), tag);
             ll_store(w + 2, (unsigned long long)__double_as_longlong(sth), tag);
         };
-        cta_linesearch_t<SEARCH_THREADS, PairCoef>(sm.pc, i_in, j_in, tab, sm.ls, res, publish);
+        cta_linesearch_t<SEARCH_THREADS, PairCoef, decltype(publish), false, false>(sm.pc, i_in, j_in, tab, sm.ls, res, publish);
         if (tid == 0) {
             const unsigned long long t = gtimer();
             t_search += t - tq;
@@ -1281,7 +1367,10 @@ __global__ void __launch_bounds__(THREADS, 1) sweep3_kernel(Params p) {
     const int cta = blockIdx.x;
     if (cta == 0) {
         SearchSmem &sm = *reinterpret_cast<SearchSmem *>(dyn);
-        if (threadIdx.x == 0) sm.fetch_abort = 0;
+        if (threadIdx.x == 0) {
+            sm.fetch_abort = 0;
+            sm.decided = -1;
+        }
         __syncthreads();
         if (threadIdx.x < SEARCH_THREADS) search_main(p, sm);
         else fetch_main(p, sm);

@@ -262,9 +262,10 @@ def audit_decisions(records: np.ndarray, blocks, pairs, mask, tables, near_tie=1
     scm = np.where(np.isfinite(strict['coarse_margin']), strict['coarse_margin'], np.inf)
     margin = np.minimum(np.minimum(fm, cm), np.minimum(sfm, scm))
     tie = margin < near_tie
+    # the pipelined sweep kernel leaves its own margins at +inf (off its critical path): the strict pass supplies them
     return dict(pairs=P, mismatches=np.nonzero(diff)[0].tolist(), near_ties=np.nonzero(tie)[0].tolist(),
-                unexplained=np.nonzero(diff & ~tie)[0].tolist(), min_fine_margin=float(fm.min()),
-                min_coarse_margin=float(cm.min()))
+                unexplained=np.nonzero(diff & ~tie)[0].tolist(), min_fine_margin=float(np.minimum(fm, sfm).min()),
+                min_coarse_margin=float(np.minimum(cm, scm).min()))
 
 
 def sweep_engine(n, na=None):
