@@ -510,8 +510,11 @@ def single_gpu_leg(args, n, steps, warmup, local_rank, detail):
     phases['sweep_flush_ms'] = timed(lambda: dev.sweep_flush(Gamma, W, n, work), 1)
     if detail:
         g, Ud = fresh_state()
-        tsum = dev.to_host(dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs, timers=True)[1])   # build with phase timers (~5 % slower)
+        trace = dev.empty(32, 16)
+        tsum = dev.to_host(dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs, timers=True, trace_out=trace,
+                                           trace_first_pair=len(pairs_np) // 2)[1])   # build with phase timers (~5 % slower)
         phases['sweep_phase_us_per_pair'] = sweep_phase_table(tsum, len(pairs_np))
+        phases['sweep_chain_us'] = chain_table(dev.to_host(trace))
         lsn = ['coarse', 'reduce', 'fine', 'scan', 'margin', 'tail']
         phases['linesearch_cycles_per_pair_cta0'] = {k: float(v) / len(pairs_np) for k, v in zip(lsn, tsum[10:16])}
         # one Newton-Raphson ("nr", the path of the reference's examples) iteration through the public API, device-resident
@@ -612,6 +615,33 @@ def measure_fp64_peak(timed):
         return tf, f'measured in this run: cuBLAS DGEMM {m}^3 (torch.matmul f64), best of 3 x 2'
     except Exception as exc:       # noqa: BLE001
         return 37.1, f'fallback: DMMA m8n8k4 microbenchmark of round 1 (in-run DGEMM failed: {exc})'
+
+
+def chain_table(trace):
+    """Averages (us) along the per-pair dependency chain from the event trace of the timed sweep kernel (csrc/sweep3.cu TR_*):
+    angle k-3 published -> worker sees it -> worker step starts -> partial of super block k posted -> reducer has all
+    partials -> total published -> prefetch warps have it -> reduced super block ready -> search k starts -> angle k published.
+    The sum is three pair periods (the lookahead is three pairs)."""
+    tr = np.asarray(trace, dtype=np.float64).reshape(-1, 16)
+    names = ['angle_to_worker', 'worker_plan_to_step_start', 'step_start_to_partial_posted', 'posted_to_reducer_has_all',
+             'reducer_sum_publish', 'published_to_prefetch_has_it', 'prefetch_contract', 'ready_to_search_start', 'search']
+    rows = []
+    for k in range(3, tr.shape[0]):
+        a, b = tr[k - 3], tr[k]
+        ev = [a[1], a[2], a[3], b[4], b[5], b[6], b[7], b[8], b[0], b[1]]
+        if min(ev) <= 0:
+            continue
+        rows.append(np.diff(np.array(ev)) / 1e3)
+    if not rows:
+        return None
+    m = np.mean(np.array(rows), axis=0)
+    out = {n_: float(v) for n_, v in zip(names, m)}
+    out['three_pair_loop_us'] = float(m.sum())
+    out['pairs_traced'] = len(rows)
+    # the raw stamps of the first 12 traced pairs, us since the first one (columns: TR_* 0..9 of csrc/sweep3.cu)
+    t0 = tr[tr > 0].min() if (tr > 0).any() else 0.0
+    out['raw_us'] = [[round((v - t0) / 1e3, 2) if v > 0 else None for v in row[:10]] for row in tr[:12]]
+    return out
 
 
 def sweep_phase_table(tsum, npairs):
@@ -786,8 +816,11 @@ def multi_gpu_leg(args, n, steps, warmup, rank, world, local_rank, peers, detail
     phases['flush_sharded_ms'], _ = tmax(lambda: st.flush(W))
     phases['step_minus_sweep_kernel_ms'] = ms_per_step - sweep_ms
     if detail:
-        tsum = dev.to_host(dev.sweep_cycle(st.gamma, st.G, Ud, W, n, pairs_d, mask, tabs, st.a0, st.na, peers, timers=True)[1])
+        trace = dev.empty(32, 16)
+        tsum = dev.to_host(dev.sweep_cycle(st.gamma, st.G, Ud, W, n, pairs_d, mask, tabs, st.a0, st.na, peers, timers=True,
+                                           trace_out=trace, trace_first_pair=len(pairs_np) // 2)[1])
         phases['sweep_phase_us_per_pair'] = sweep_phase_table(tsum, len(pairs_np))
+        phases['sweep_chain_us'] = chain_table(dev.to_host(trace))
     peak, peak_src = hbm_peak()
     acc_mask = rs['accepted'] != 0
     algo_bytes = 16.0 * (n ** 4 - (n - 2) ** 4) * n_acc / world

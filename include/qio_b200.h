@@ -223,6 +223,12 @@ typedef struct qio_b200_sweep_options {
     double *blocks_out;          /* DEVICE (P, QIO_B200_BLOCK_DOUBLES) or NULL: the pair block every line search of the
                                     cycle ran on -- feeding it to qio_b200_pair_linesearch(strict_order = 1) re-derives
                                     every decision of the cycle in the reference's own operation order (decision audit) */
+    double *trace_out;           /* DEVICE (32, 16) or NULL, timers build only: globaltimer stamps (ns) of ten events along the
+                                    per-pair dependency chain (search start, angle published, worker saw it / started / posted
+                                    its partial, reducer got all partials / published, prefetch got the total / finished) for
+                                    the 32 pairs starting at trace_first_pair (profiling aid; csrc/sweep3.cu TR_*) */
+    int32_t trace_first_pair;
+    int32_t reserved;
 } qio_b200_sweep_options;
 size_t qio_b200_sweep_workspace_bytes(int n);
 /* Which kernel sweep_cycle runs by default for (n, na): 3 = pipelined (no grid barriers: column-owning worker CTAs, reducer

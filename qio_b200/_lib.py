@@ -42,7 +42,8 @@ class ThetaTables(ctypes.Structure):
 class SweepOptions(ctypes.Structure):
     """struct qio_b200_sweep_options (all zero = defaults)"""
     _fields_ = [('engine', ctypes.c_int32), ('timers', ctypes.c_int32), ('timeout_ms', ctypes.c_uint32),
-                ('startup_timeout_ms', ctypes.c_uint32), ('blocks_out', ctypes.c_void_p)]
+                ('startup_timeout_ms', ctypes.c_uint32), ('blocks_out', ctypes.c_void_p), ('trace_out', ctypes.c_void_p),
+                ('trace_first_pair', ctypes.c_int32), ('reserved', ctypes.c_int32)]
 
 
 class Peers(ctypes.Structure):

@@ -91,6 +91,8 @@ struct Params {
     unsigned long long *tot;    // [SLOTS][TOT_WORDS][2] tagged totals, tag = k + 1
     unsigned long long timeout_ns, startup_timeout_ns;
     double *blocks_out;         // (P, 24) or NULL: the block each search ran on (decision audit)
+    double *trace;              // timed build only, or NULL: [TRACE_PAIRS][TRACE_EVENTS] globaltimer stamps (ns) of the pairs
+    int trace_k0;               //   trace_k0 .. trace_k0 + TRACE_PAIRS - 1 (see the TR_* constants)
     int rank, nranks;
     unsigned epoch;             // launch epoch of the mailbox tags (ll.cuh: mailbox_tag)
     double *const *mailboxes;   // [nranks] bases, layout [MB_SLOTS][nranks][SB_MAX][2]
@@ -107,6 +109,28 @@ __device__ __forceinline__ unsigned long long wtimer() {     // watchdog clock: 
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
+}
+// Event trace of the timed build: who saw what when, for a window of pairs (the per-pair dependency chain made visible).
+constexpr int TRACE_PAIRS = 32, TRACE_EVENTS = 16;
+enum { TR_SEARCH_START = 0,   // search CTA: super block k is there, contraction starts
+       TR_DECIDED = 1,        // search CTA: angle k published
+       TR_W_ANGLE = 2,        // worker 0 planner: angle k seen
+       TR_W_START = 3,        // worker 0: step k starts (rotation k, produces super block k + 3)
+       TR_W_POSTED = 4,       // worker 0: partial of super block k posted  (stored under pair k, written during step k - 3)
+       TR_R_GOT = 5,          // reducer 0: all partials of super block k seen
+       TR_R_PUB = 6,          // reducer 0: total of super block k published
+       TR_F_GOT = 7,          // prefetch warps: total(s) of super block k seen
+       TR_F_DONE = 8,         // prefetch warps: reduced super block k ready (full barrier arrives)
+       TR_W_END = 9 };        // worker 0: step k done
+template <typename P_>
+__device__ __forceinline__ void trace_event(const P_ &p, int k, int ev) {
+#ifdef QIO_S3_TIMED
+    if (p.trace && k >= p.trace_k0 && k < p.trace_k0 + TRACE_PAIRS) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[(size_t)(k - p.trace_k0) * TRACE_EVENTS + ev] = (double)t;
+    }
+#endif
 }
 __device__ __forceinline__ unsigned long long gtimer() {     // phase timers: only in the QIO_S3_TIMED build
 #ifndef QIO_S3_TIMED
@@ -449,6 +473,7 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
     const double c = st.c, s = st.s;
     const int i = st.i, j = st.j, m = st.m, e = st.e, pitch = p.wc_cols;
     const unsigned long long t_begin = (widx == 0 && tid == 0) ? gtimer() : 0;
+    if (widx == 0 && tid == 0) trace_event(p, st.slot - LOOK, TR_W_START);
     auto bf = [&](VT &x, VT &y) {
         if constexpr (V == 2) {
             const VT nx_ = make_double2(c * x.x + s * y.x, c * x.y + s * y.y);
@@ -698,11 +723,15 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
             for (int en = tid; en < m * m3; en += TILE_THREADS) post_entry(en);
         }
     }
-    if (widx == 0 && tid == 0) sm.t_tile += gtimer() - t_begin;
+    if (widx == 0 && tid == 0) {
+        sm.t_tile += gtimer() - t_begin;
+        trace_event(p, st.slot, TR_W_POSTED);
+    }
 
     // ---- flat phase: every other row pair of rotation (i, j) inside the owned columns ----------------------------
     if (rot) flat_update<V>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, tid, WORK_THREADS);
     if (tm2) sm.t_flat += gtimer() - t_b2;
+    if (widx == 0 && tid == 0) trace_event(p, st.slot - LOOK, TR_W_END);
 }
 
 // The planner warp of a worker: the plan of step w (rotation w, super block w + LOOK); w < 0: the prologue super blocks
@@ -743,6 +772,7 @@ __device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm
             const unsigned long long tw0 = gtimer();
             alive = read_record(p, w, acc, c, s) ? 1 : 0;
             sm.t_wait += gtimer() - tw0;
+            if (blockIdx.x == FIRST_WORKER) trace_event(p, w, TR_W_ANGLE);
         }
         alive = __shfl_sync(0xffffffffu, alive, 0);
         acc = __shfl_sync(0xffffffffu, acc, 0);
@@ -916,23 +946,25 @@ __device__ __forceinline__ void reducer_main(const Params &p, double *scratch /*
         const int slot = k & (SLOTS - 1);
         const int m = p.dtab[(size_t)k * DT_STRIDE];
         const int ne = m * m * m * m, e_lo = ne * ridx / NRED, e_hi = ne * (ridx + 1) / NRED, nl = e_hi - e_lo;
-        // `ns` sub-sums per entry over interleaved subsets of the workers: every thread has 8 tagged loads in flight and
-        // re-polls a batch until all its tags are those of super block k
+        // `ns` sub-sums per entry over interleaved subsets of the workers: every thread has RLD tagged loads in flight and
+        // re-polls a batch until all its tags are those of super block k (with 142 workers and ns = 8 the whole column of an
+        // entry is two round trips through L2)
+        constexpr int RLD = 12;
         const int ns = nl > 0 ? max(1, min(8, THREADS / nl)) : 1;
         const unsigned want = (unsigned)(k + 1);
         const unsigned long long *pb = p.pbuf + (size_t)slot * p.nworkers * SB_MAX * 2;
         bool ok = true;
         for (int it = tid; it < nl * ns; it += THREADS) {
             const int el = it % nl, sub = it / nl;
-            double a8[8];
+            double a8[RLD];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) a8[u] = 0.0;
-            for (int w0 = sub; w0 < p.nworkers; w0 += 8 * ns) {
-                unsigned long long v[8];
+            for (int u = 0; u < RLD; ++u) a8[u] = 0.0;
+            for (int w0 = sub; w0 < p.nworkers; w0 += RLD * ns) {
+                unsigned long long v[RLD];
                 ok &= spin_until(p, [&]() {
                     bool all = true;
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < RLD; ++u) {
                         const int wk = w0 + u * ns;
                         if (wk < p.nworkers) all &= ll_load(pb + ((size_t)wk * SB_MAX + e_lo + el) * 2, v[u], want);
                         else v[u] = 0ull;
@@ -940,21 +972,23 @@ __device__ __forceinline__ void reducer_main(const Params &p, double *scratch /*
                     return all;
                 });
 #pragma unroll
-                for (int u = 0; u < 8; ++u) a8[u] += __longlong_as_double((long long)v[u]);
+                for (int u = 0; u < RLD; ++u) a8[u] += __longlong_as_double((long long)v[u]);
             }
+            // fixed summation tree (independent of arrival order): 12 -> 6 -> 3 -> 1
 #pragma unroll
-            for (int w = 4; w > 0; w >>= 1)
+            for (int u = 0; u < 6; ++u) a8[u] += a8[u + 6];
 #pragma unroll
-                for (int u = 0; u < w; ++u) a8[u] += a8[u + w];
-            scratch[sub * SB_MAX + el] = a8[0];
+            for (int u = 0; u < 3; ++u) a8[u] += a8[u + 3];
+            scratch[sub * SB_MAX + el] = (a8[0] + a8[1]) + a8[2];
         }
         if (!ok) flag_sm[0] = -1;
+        __syncthreads();
         if (tid == 0) {
             const unsigned long long t = gtimer();
             t_wait += t - tq;
             tq = t;
+            if (ridx == 0) trace_event(p, k, TR_R_GOT);
         }
-        __syncthreads();
         if (flag_sm[0] < 0) return;
         for (int el = tid; el < nl; el += THREADS) {
             double total = scratch[el];
@@ -977,6 +1011,7 @@ __device__ __forceinline__ void reducer_main(const Params &p, double *scratch /*
             const unsigned long long t = gtimer();
             t_red += t - tq;
             tq = t;
+            if (ridx == 0) trace_event(p, k, TR_R_PUB);
         }
     }
     if (ridx == 0 && tid == 0) {
@@ -1095,6 +1130,26 @@ __device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
         const int ne = m_k * m_k * m_k * m_k, ng = 2 * m_k * m_k;
         const int pos_i = dt[7], pos_j = dt[8], pa0 = dt[9], pb0 = dt[10], pa1 = dt[11], pb1 = dt[12];
         bool ok = true;
+        if (p.nranks == 1) {
+            // one rank: every word this thread is responsible for (<= 8) is polled in the same round trip
+            constexpr int FMAX = (TOT_WORDS + FETCH_THREADS - 1) / FETCH_THREADS;
+            const unsigned long long *tb = p.tot + (size_t)(k & (SLOTS - 1)) * TOT_WORDS * 2;
+            unsigned long long v[FMAX];
+            ok &= spin_until(p, [&]() {
+                bool all = true;
+#pragma unroll
+                for (int u = 0; u < FMAX; ++u) {
+                    const int e = ft + u * FETCH_THREADS;
+                    if (e < ne + ng) all &= ll_load(tb + (size_t)(e >= ne ? SB_MAX + (e - ne) : e) * 2, v[u], (unsigned)(k + 1));
+                }
+                return all;
+            });
+#pragma unroll
+            for (int u = 0; u < FMAX; ++u) {
+                const int e = ft + u * FETCH_THREADS;
+                if (e < ne + ng) sm.sb[e >= ne ? SB_MAX + (e - ne) : e] = __longlong_as_double((long long)v[u]);
+            }
+        } else
         for (int e = ft; e < ne + ng; e += FETCH_THREADS) {
             const bool is_g = e >= ne;
             const int word = is_g ? SB_MAX + (e - ne) : e;
@@ -1137,6 +1192,7 @@ __device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
         if (!ok) sm.fetch_abort = 1;
         if (k == 0 && ft == 0 && ok) atomicExch(p.abort_flag + 1, 1u);      // start-up is over: the normal time-out applies
         named_sync<6, FETCH_THREADS>();
+        if (ft == 0) trace_event(p, k, TR_F_GOT);       // every word of the super block (and angle k - 2) is here
         if (!sm.fetch_abort) {
             // Y: the orbitals of pairs k-1 and k, as positions in D_k, in order of first appearance
             // (kept in scalars and selected with compares: a runtime-indexed array would live in local memory)
@@ -1162,13 +1218,17 @@ __device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
                 else { pA = pos; cA = 1.0; pB = pos; cB = 0.0; }
             };
             const int m = m_k, n1 = nY, n2 = nY * nY, n3 = n2 * nY;
+            // Each pass: one thread per output column (everything but the new index), looping over the new index y, so that
+            // the index arithmetic is one division per thread and pass instead of one per output.
             // pass 1 (index s): z0[pqr][y4]; the gamma part alongside: sbp[256 + spin*16 + y*4 + y']
-            for (int o = ft; o < m * m * m * n1; o += FETCH_THREADS) {
-                const int pqr = o / n1, y4 = o - pqr * n1;
-                int pA, pB;
-                double cA, cB;
-                g0row(y4, pA, cA, pB, cB);
-                sm.z[0][o] = cA * sm.sb[pqr * m + pA] + cB * sm.sb[pqr * m + pB];
+            for (int pqr = ft; pqr < m * m * m; pqr += FETCH_THREADS) {
+                const double *src = sm.sb + pqr * m;
+                for (int y4 = 0; y4 < n1; ++y4) {
+                    int pA, pB;
+                    double cA, cB;
+                    g0row(y4, pA, cA, pB, cB);
+                    sm.z[0][pqr * n1 + y4] = cA * src[pA] + cB * src[pB];
+                }
             }
             for (int o = ft; o < 2 * n2; o += FETCH_THREADS) {
                 const int spin = o / n2, r = o - spin * n2, y = r / n1, yy = r - y * n1;
@@ -1181,31 +1241,37 @@ __device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
                     cA * (dA * gm[pA * m + qA] + dB * gm[pA * m + qB]) + cB * (dA * gm[pB * m + qA] + dB * gm[pB * m + qB]);
             }
             named_sync<6, FETCH_THREADS>();
-            // pass 2 (index r): z1[pq][y3][y4]
-            for (int o = ft; o < m * m * n2; o += FETCH_THREADS) {
-                const int pq = o / n2, r = o - pq * n2, y3 = r / n1, y4 = r - y3 * n1;
-                int pA, pB;
-                double cA, cB;
-                g0row(y3, pA, cA, pB, cB);
-                sm.z[1][o] = cA * sm.z[0][(pq * m + pA) * n1 + y4] + cB * sm.z[0][(pq * m + pB) * n1 + y4];
+            // pass 2 (index r): z1[pq][y3][y4]; thread <-> (pq, y4)
+            for (int t = ft; t < m * m * n1; t += FETCH_THREADS) {
+                const int pq = t / n1, y4 = t - pq * n1;
+                for (int y3 = 0; y3 < n1; ++y3) {
+                    int pA, pB;
+                    double cA, cB;
+                    g0row(y3, pA, cA, pB, cB);
+                    sm.z[1][pq * n2 + y3 * n1 + y4] = cA * sm.z[0][(pq * m + pA) * n1 + y4] + cB * sm.z[0][(pq * m + pB) * n1 + y4];
+                }
             }
             named_sync<6, FETCH_THREADS>();
-            // pass 3 (index q): z0[p][y2][y3 y4]
-            for (int o = ft; o < m * n3; o += FETCH_THREADS) {
-                const int pp = o / n3, r = o - pp * n3, y2 = r / n2, rest = r - y2 * n2;
-                int pA, pB;
-                double cA, cB;
-                g0row(y2, pA, cA, pB, cB);
-                sm.z[0][o] = cA * sm.z[1][(pp * m + pA) * n2 + rest] + cB * sm.z[1][(pp * m + pB) * n2 + rest];
+            // pass 3 (index q): z0[p][y2][y3 y4]; thread <-> (p, y3 y4)
+            for (int t = ft; t < m * n2; t += FETCH_THREADS) {
+                const int pp = t / n2, rest = t - pp * n2;
+                for (int y2 = 0; y2 < n1; ++y2) {
+                    int pA, pB;
+                    double cA, cB;
+                    g0row(y2, pA, cA, pB, cB);
+                    sm.z[0][pp * n3 + y2 * n2 + rest] = cA * sm.z[1][(pp * m + pA) * n2 + rest] + cB * sm.z[1][(pp * m + pB) * n2 + rest];
+                }
             }
             named_sync<6, FETCH_THREADS>();
-            // pass 4 (index p): sbp[y1][y2][y3][y4] with stride MAXY
-            for (int o = ft; o < n1 * n3; o += FETCH_THREADS) {
-                const int y1 = o / n3, r = o - y1 * n3, y2 = r / n2, r2 = r - y2 * n2, y3 = r2 / n1, y4 = r2 - y3 * n1;
-                int pA, pB;
-                double cA, cB;
-                g0row(y1, pA, cA, pB, cB);
-                sm.sbp[b][((y1 * MAXY + y2) * MAXY + y3) * MAXY + y4] = cA * sm.z[0][pA * n3 + r] + cB * sm.z[0][pB * n3 + r];
+            // pass 4 (index p): sbp[y1][y2][y3][y4] with stride MAXY; thread <-> (y2, y3, y4)
+            for (int r = ft; r < n3; r += FETCH_THREADS) {
+                const int y2 = r / n2, r2 = r - y2 * n2, y3 = r2 / n1, y4 = r2 - y3 * n1;
+                for (int y1 = 0; y1 < n1; ++y1) {
+                    int pA, pB;
+                    double cA, cB;
+                    g0row(y1, pA, cA, pB, cB);
+                    sm.sbp[b][((y1 * MAXY + y2) * MAXY + y3) * MAXY + y4] = cA * sm.z[0][pA * n3 + r] + cB * sm.z[0][pB * n3 + r];
+                }
             }
             if (ft == 0) {
                 int *mt = sm.meta[b];
@@ -1218,7 +1284,10 @@ __device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
             }
         }
         named_sync<6, FETCH_THREADS>();
-        if (ft == 0) sm.sb_ok[b] = sm.fetch_abort ? 0 : 1;
+        if (ft == 0) {
+            sm.sb_ok[b] = sm.fetch_abort ? 0 : 1;
+            trace_event(p, k, TR_F_DONE);
+        }
         __threadfence_block();
         named_arrive_id<THREADS>(2 + b);                    // full[b]
         if (sm.fetch_abort) {
@@ -1257,6 +1326,7 @@ __device__ __forceinline__ void search_main(const Params &p, SearchSmem &sm) {
             const unsigned long long t = gtimer();
             t_wait += t - tq;
             tq = t;
+            trace_event(p, k, TR_SEARCH_START);
         }
         const int *mt = sm.meta[b];
         const bool i_in = mt[2] != 0, j_in = mt[3] != 0;
@@ -1324,6 +1394,7 @@ __device__ __forceinline__ void search_main(const Params &p, SearchSmem &sm) {
             sm.hist_s[k & 3] = sth;
             __threadfence_block();
             *reinterpret_cast<volatile int *>(&sm.decided) = k;
+            trace_event(p, k, TR_DECIDED);
             unsigned long long *w = p.ring + (size_t)(k & (RING - 1)) * 4;
             const unsigned tag = 2u * (unsigned)(k + 1) + (accepted ? 1u : 0u);
             ll_store(w, (unsigned long long)__double_as_longlong(cth), tag);
@@ -1485,6 +1556,9 @@ int S3_LAUNCH(double *gamma, double *S, double *U, double *W, int n, int a0, int
     p.timeout_ns = 1000000ull * (opts.timeout_ms ? opts.timeout_ms : 4000u);
     p.startup_timeout_ns = 1000000ull * (opts.startup_timeout_ms ? opts.startup_timeout_ms : 60000u);
     p.blocks_out = opts.blocks_out;
+    p.trace = opts.trace_out;
+    p.trace_k0 = opts.trace_first_pair;
+    if (p.trace) QIO_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(double) * TRACE_PAIRS * TRACE_EVENTS, st));
     p.dtab = reinterpret_cast<const int32_t *>(ws + L.off_dtab);
     p.wg = reinterpret_cast<double *>(ws + L.off_wg);
     p.rg = reinterpret_cast<double *>(ws + L.off_rg);

@@ -220,7 +220,7 @@ def sweep_reset(W, n):
 
 
 def sweep_cycle(gamma, S, U, W, n, pairs, mask, tables, a0=0, na=None, peers=None, engine=0, timers=False,
-                blocks_out=None, timeout_ms=0, startup_timeout_ms=0):
+                blocks_out=None, timeout_ms=0, startup_timeout_ms=0, trace_out=None, trace_first_pair=0):
     """One cycle on the deferred-axis state (S, W); returns (results bytes, summary).
     ``peers`` is a qio_b200.peers.PeerGroup (multi-GPU) or None.  ``engine``: 0 = automatic, 2 = barrier kernel,
     3 = pipelined kernel; ``timers``: the build that carries phase timers; ``blocks_out``: (P, 24) device tensor that
@@ -234,7 +234,8 @@ def sweep_cycle(gamma, S, U, W, n, pairs, mask, tables, a0=0, na=None, peers=Non
     if peers is not None:
         peers.next_epoch()
     opts = _lib.SweepOptions(int(engine), 1 if timers else 0, int(timeout_ms), int(startup_timeout_ms),
-                             0 if blocks_out is None else blocks_out.data_ptr())
+                             0 if blocks_out is None else blocks_out.data_ptr(),
+                             0 if trace_out is None else trace_out.data_ptr(), int(trace_first_pair), 0)
     check(lib.qio_b200_sweep_cycle(_ptr(gamma), _ptr(S), _ptr(U), _ptr(W), n, a0, na, _ptr(pairs), P, _ptr(mask),
                                     ctypes.byref(tables.struct), _ptr(results), _ptr(summary), _ptr(ws),
                                     ctypes.byref(peers.struct) if peers is not None else None, ctypes.byref(opts),

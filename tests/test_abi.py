@@ -37,7 +37,7 @@ def test_struct_layouts_match():
     assert _lib.LS_DTYPE.itemsize == 80
     assert _lib.LS_DTYPE.fields['theta'][1] == 16 and _lib.LS_DTYPE.fields['cos_theta'][1] == 56
     assert ctypes.sizeof(_lib.ThetaTables) == 8 + 5 * 8
-    assert ctypes.sizeof(_lib.SweepOptions) == 4 * 4 + 8 and _lib.SweepOptions.blocks_out.offset == 16
+    assert ctypes.sizeof(_lib.SweepOptions) == 4 * 4 + 8 + 8 + 8 and _lib.SweepOptions.blocks_out.offset == 16
     assert ctypes.sizeof(_lib.Peers) == 4 * 4 + 8
     assert _lib.lib.qio_b200_abi_version() == 2
 
