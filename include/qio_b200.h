@@ -89,6 +89,9 @@ int qio_b200_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * operation is shard-local).  dm1/gamma may be NULL to skip the 1-RDM. */
 int qio_b200_prep_rdm12(const double *dm1, const double *dm2, double *gamma, double *Gamma,
                         int n, int na, void *stream);
+/* Self-test of the three-operation correctly rounded x / 6 the prep kernel uses (csrc/prep.cu div6_rn) against the IEEE
+ * division: 2 * count pseudo-random doubles; *bad (device) receives the number of results that differ in any bit. */
+int qio_b200_selftest_div6(unsigned long long count, unsigned long long seed, unsigned long long *bad, void *stream);
 
 /* ---- a-2/a-3  qio/entropy.py:4-47  shannon / get_cost_fqi ----------------------------------
  * diag (3, m): nu = gamma[2k,2k], nd = gamma[2k+1,2k+1], nn = Gamma[k,k,k,k] for k = inds[t];

@@ -69,6 +69,7 @@ SIGNATURES = {
     'qio_b200_abi_version': ([], _i),
     'qio_b200_device_info': ([_p, _p, _p], _i),
     'qio_b200_prep_rdm12': ([_p, _p, _p, _p, _i, _i, _p], _i),
+    'qio_b200_selftest_div6': ([ctypes.c_ulonglong, ctypes.c_ulonglong, _p, _p], _i),
     'qio_b200_orbital_diagonals': ([_p, _p, _i, _i, _i, _p, _i, _p, _p], _i),
     'qio_b200_orbital_entropies': ([_p, _i, _p, _p, _p, _p, _p], _i),
     'qio_b200_shannon': ([_p, _ll, _p, _p], _i),

@@ -22,9 +22,7 @@
 //   * batched: `batch` independent problems of the same shape (the slabs of a leading-index shard, qio_b200_rotate_axis_batched)
 //     are one launch -- the tensor map has the batch as its fourth dimension and the persistent tile loop runs over
 //     (batch, M tile).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tma.cuh"
 
 namespace qio {
 
@@ -37,35 +35,6 @@ constexpr int RT_MAX_NT = 7;          // n8-tiles of the wider warp column
 constexpr int RT_MAX_COLS = 8 * (2 * RT_MAX_NT - 1);   // 104 columns per CTA
 constexpr int RT_MAX_STAGES = 8;
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, unsigned long long *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-        : "memory");
-}
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
@@ -96,7 +65,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
             mbar_init(full + s, 1);
             mbar_init(empty + s, RT_CONSUMERS / 32);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     // B: sB[k][c] = U[n0 + c][k], zero beyond (kdim, ncols)
     for (int e = tid; e < kpad * np; e += RT_THREADS) {
@@ -194,10 +163,6 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static EncodeTiledFn lookup_encode_tiled() {
     void *p = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -206,7 +171,7 @@ static EncodeTiledFn lookup_encode_tiled() {
         return reinterpret_cast<EncodeTiledFn>(p);
     return nullptr;
 }
-static EncodeTiledFn encode_tiled_fn() {
+EncodeTiledFn encode_tiled_fn() {
     static const EncodeTiledFn fn = lookup_encode_tiled();      // driver entry point: thread-safe one-time lookup
     return fn;
 }

@@ -35,7 +35,9 @@ def rotated_case(n, seed=5, np_seed=1):
 
 
 # ---- a-1 ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('n', [1, 2, 6, 12, 31, 32, 33, 40, 52, 53, 54, 60])   # 53+: several 52-wide tiles, ragged last tile
+# odd n and n < 16: the cp-style kernel (53+: several 52-wide tiles, ragged last tile); even n >= 16: the TMA kernel (64-wide tile
+# pairs combined in place: one tile, exactly one tile, ragged second tile, three tiles)
+@pytest.mark.parametrize('n', [1, 2, 6, 12, 16, 18, 31, 32, 33, 40, 52, 53, 54, 60, 64, 66, 80, 130])
 def test_prep_rdm12_bit_exact(n):
     rng = np.random.default_rng(n)
     dm1 = rng.standard_normal((n, n))
@@ -45,6 +47,37 @@ def test_prep_rdm12_bit_exact(n):
     assert isinstance(G, np.ndarray) and np.array_equal(g, g_ref) and np.array_equal(G, G_ref)
     gd, Gd = prep_rdm12(dev.to_device(dm1), dev.to_device(dm2))
     assert dev.is_device(Gd) and np.array_equal(dev.to_host(Gd), G_ref) and np.array_equal(dev.to_host(gd), g_ref)
+
+
+def test_div6_three_operation_division_is_ieee_division():
+    """The prep kernel divides by 6 with q0 = x * RN(1/6), r = fma(-6, q0, x), q = fma(r, RN(1/6), q0): bit-identical to
+    the IEEE division on 2 x 2e9 pseudo-random doubles (all exponents, and the range RDM entries live in)."""
+    bad = torch.zeros(1, dtype=torch.int64, device='cuda')
+    from qio_b200._lib import check, lib
+    check(lib.qio_b200_selftest_div6(2_000_000_000, 12345, bad.data_ptr(), None), 'selftest_div6')
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+
+
+def test_prep_rdm12_special_values():
+    """Zeros (both signs), subnormals, huge values, infinities and NaNs go through the same combination as numpy's."""
+    n = 16
+    rng = np.random.default_rng(0)
+    dm2 = rng.standard_normal((n, n, n, n))
+    flat = dm2.reshape(-1)
+    flat[::7] = 0.0
+    flat[1::11] = -0.0
+    flat[2::13] = 5e-324
+    flat[3::17] = 1e-310
+    flat[4::19] = 1e305
+    flat[5::23] = np.inf
+    flat[6::29] = np.nan
+    flat[8::31] = 2.0 ** -1000
+    with np.errstate(all='ignore'):
+        _, G_ref = O.prep_rdm12(np.eye(n), dm2)
+    _, G = prep_rdm12(np.eye(n), dm2)
+    assert np.array_equal(G, G_ref, equal_nan=True)
+    assert np.array_equal(np.signbit(G[~np.isnan(G)]), np.signbit(G_ref[~np.isnan(G_ref)]))
 
 
 def test_prep_rdm12_golden(golden6, golden12):
