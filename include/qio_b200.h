@@ -176,6 +176,13 @@ int qio_b200_rotate_axis_batched(const double *U, const double *in, double *out,
                                  long long ld_in, int batch, long long batch_stride_in, long long batch_stride_out,
                                  void *stream);
 
+/* Rectangular cyclic pass (qio/solver/tccsd.py:157-158,164-172: the amplitude projections
+ * 'ijab,Ii,Jj,Aa,Bb->IJAB' between the CAS and the CCSD orbital spaces are four of these):
+ *   out[m, i] = sum_{k < kdim} U[i * ldu + k] in[k, m],   in (kdim, rows) -> out (rows, n_out):
+ * the leading axis (length kdim) is contracted with the n_out x kdim matrix U and re-appears as the last axis. */
+int qio_b200_contract_axis_cyclic(const double *U, long long ldu, const double *in, double *out, int n_out,
+                                  int kdim, long long rows, void *stream);
+
 /* Single-axis contraction that keeps the index order (used to flush the deferred sweep state):
  *   last_axis == 0:  out[i, m] = sum_a U[i, a] in[a, m]   in, out are (n, rows)
  *   last_axis != 0:  out[m, i] = sum_d in[m, d] U[i, d]   in, out are (rows, n)              */

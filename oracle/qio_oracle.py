@@ -587,3 +587,53 @@ def reorder(gamma, Gamma, N_cas):
             for ii in range(jj):
                 swap(jj - 1 - ii)
     return swaps, n_closed, V
+
+
+# ----------------------------------------------------------------------------------------
+# Dense linear algebra of the TCCSD wrapper                      qio/solver/tccsd.py:153-267
+# ----------------------------------------------------------------------------------------
+def tccsd_project_t1(t1, pocc, pvir, to_cas=False):
+    """einsum('ia,Ii,Aa->IA') (tccsd.py:153,170) or, to_cas, einsum('IA,Ii,Aa->ia') (tccsd.py:164)."""
+    return np.einsum('IA,Ii,Aa->ia', t1, pocc, pvir) if to_cas else np.einsum('ia,Ii,Aa->IA', t1, pocc, pvir)
+
+
+def tccsd_project_t2(t2, pocc, pvir, to_cas=False):
+    """einsum('ijab,Ii,Jj,Aa,Bb->IJAB') (tccsd.py:154,171) or, to_cas, einsum('IJAB,Ii,Jj,Aa,Bb->ijab') (tccsd.py:165)."""
+    if to_cas:
+        return np.einsum('IJAB,Ii,Jj,Aa,Bb->ijab', t2, pocc, pocc, pvir, pvir, optimize='optimal')
+    return np.einsum('ijab,Ii,Jj,Aa,Bb->IJAB', t2, pocc, pocc, pvir, pvir, optimize='optimal')
+
+
+def tccsd_tailor(t1, t2, t1cas_fci, t2cas_fci, pocc, pvir):
+    """The body of ``callback`` (tccsd.py:160-175) on copies: returns the tailored (t1, t2)."""
+    t1cas_cc = tccsd_project_t1(t1, pocc, pvir, to_cas=True)
+    t2cas_cc = tccsd_project_t2(t2, pocc, pvir, to_cas=True)
+    dt1 = tccsd_project_t1(t1cas_fci - t1cas_cc, pocc, pvir)
+    dt2 = tccsd_project_t2(t2cas_fci - t2cas_cc, pocc, pvir)
+    return t1 + dt1, t2 + dt2
+
+
+def make_no(rdm1, mo_coeff, subspace=None):
+    """Natural orbitals (tccsd.py:209-244).  With a subspace the reference's ``rdm1_new[subspace,:][:,subspace] = ...``
+    assigns into a temporary (:238), so rdm1_new is an unchanged copy."""
+    if subspace is not None:
+        sub = rdm1[subspace, :][:, subspace]
+        csub = mo_coeff[:, subspace]
+    else:
+        sub, csub = rdm1, mo_coeff
+    e, v = np.linalg.eigh(sub)
+    v = v[:, np.argsort(e)[::-1]]
+    no_sub = csub @ v
+    if subspace is not None:
+        no = mo_coeff.copy()
+        no[:, subspace] = no_sub
+        return no, rdm1.copy()
+    return no_sub, np.diag(np.ones(len(rdm1)) * 2)
+
+
+def semi_canonicalize(fock_ao, mo_coeff, nocc):
+    """Semi-canonical MO coefficients (tccsd.py:247-267); takes the AO Fock matrix itself instead of ``mf``."""
+    fockmo = mo_coeff.conj().T @ fock_ao @ mo_coeff
+    _, vo = np.linalg.eigh(fockmo[:nocc, :nocc])
+    _, vv = np.linalg.eigh(fockmo[nocc:, nocc:])
+    return np.concatenate((mo_coeff[:, :nocc] @ vo, mo_coeff[:, nocc:] @ vv), axis=1)

@@ -17,7 +17,7 @@ from __future__ import annotations
 import sys
 
 from . import _lib  # noqa: F401  (loads the CUDA library; ImportError if missing)
-from . import device, entropy, grad, qio, synth, tables  # noqa: F401
+from . import device, entropy, grad, qio, solver, synth, tables  # noqa: F401
 from ._lib import QioCudaError  # noqa: F401
 
 __version__ = '0.1.0'
@@ -36,5 +36,7 @@ def install_as_qio():
     sys.modules['qio.grad'] = grad
     sys.modules['qio.grad.jacobi'] = grad.jacobi
     sys.modules['qio.grad.gradient'] = grad.gradient
+    # qio.solver is NOT replaced: the pyscf / block2 wrappers stay the reference's own (qio_b200.solver.tccsd only offers
+    # device versions of their dense contractions)
     return this
 from . import mutual_info  # noqa: E402,F401  (extension: two-orbital RDM / mutual information)

@@ -85,6 +85,7 @@ SIGNATURES = {
     'qio_b200_rotate_axis': ([_p, _p, _p, _i, _ll, _ll, _p], _i),
     'qio_b200_rotate_axis_batched': ([_p, _p, _p, _i, _ll, _ll, _i, _ll, _ll, _p], _i),
     'qio_b200_contract_axis': ([_p, _p, _p, _i, _ll, _i, _p], _i),
+    'qio_b200_contract_axis_cyclic': ([_p, _ll, _p, _p, _i, _i, _ll, _p], _i),
     'qio_b200_contract_axis_partial': ([_p, _ll, _p, _p, _i, _i, _ll, _p], _i),
     'qio_b200_sweep_workspace_bytes': ([_i], ctypes.c_size_t),
     'qio_b200_sweep_engine': ([_i, _i], _i),

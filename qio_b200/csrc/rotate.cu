@@ -313,6 +313,15 @@ extern "C" int qio_b200_contract_axis_partial(const double *U, long long ldu, co
     return dispatch_rotate_axis<MODE_LEAD_KEEP>(U, in, out, n, kdim, ldu, rows, rows, rows, as_stream(stream));
 }
 
+extern "C" int qio_b200_contract_axis_cyclic(const double *U, long long ldu, const double *in, double *out, int n_out,
+                                             int kdim, long long rows, void *stream) {
+    using namespace qio;
+    QIO_REQUIRE(n_out > 0 && kdim > 0 && rows >= 0 && ldu >= kdim, "contract_axis_cyclic: bad sizes");
+    if (rows == 0) return QIO_B200_OK;
+    QIO_REQUIRE(U && in && out && in != out, "contract_axis_cyclic: bad pointers");
+    return dispatch_rotate_axis<MODE_CYCLIC>(U, in, out, n_out, kdim, ldu, rows, rows, n_out, as_stream(stream));
+}
+
 extern "C" int qio_b200_rotate_rdm2(const double *U, double *Gamma, double *work, int n, void *stream) {
     using namespace qio;
     QIO_REQUIRE(n > 0 && U && Gamma && work && Gamma != work, "rotate_rdm2: bad arguments");

@@ -208,6 +208,13 @@ def contract_axis(U, src, dst, n, rows, last_axis):
     return dst
 
 
+def contract_axis_cyclic(U, src, dst, n_out, kdim, rows):
+    """dst[m, i] = sum_{k<kdim} U[i, k] src[k, m]: src (kdim, rows) -> dst (rows, n_out), U (n_out, kdim) row-major."""
+    check(lib.qio_b200_contract_axis_cyclic(_ptr(U), int(kdim), _ptr(src), _ptr(dst), int(n_out), int(kdim), int(rows), _stream()),
+          'contract_axis_cyclic')
+    return dst
+
+
 def contract_axis_partial(U, ldu, src, dst, n, kdim, rows):
     """dst[i, m] = sum_{k<kdim} U[i*ldu + k] src[k, m] (U may be a column block of a larger matrix)."""
     check(lib.qio_b200_contract_axis_partial(_ptr(U), int(ldu), _ptr(src), _ptr(dst), n, int(kdim), int(rows), _stream()),
