@@ -741,7 +741,8 @@ __device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm
     unsigned *skipmask = sm.skipmask[buf];
     const int lane = threadIdx.x & 31;
     int slot = w + LOOK;        // w = -3, -2, -1: super blocks 0, 1, 2 of the initial state
-    // everything that depends on the pair list only comes first: it overlaps the wait for the angle
+    // Everything that depends on the pair list only comes first and overlaps the wait for the angle -- including the row
+    // list of the flat phase, which is only used when the rotation is accepted and is therefore built for that case.
     int m = 0, Dq = -1;
     if (slot < p.P) {
         m = p.dtab[(size_t)slot * DT_STRIDE];
@@ -763,58 +764,25 @@ __device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm
     }
     __syncwarp();
     skipmask[lane] = sm.dorm[lane];             // MAXN3 / 32 = 32 words: one per lane
-    int i = 0, j = 0, acc = 0, alive = 1;
-    double c = 1.0, s = 0.0;
+    int i = 0, j = 0;
     if (w >= 0) {
         i = p.pairs[2 * w];
         j = p.pairs[2 * w + 1];
-        if (lane == 0) {
-            const unsigned long long tw0 = gtimer();
-            alive = read_record(p, w, acc, c, s) ? 1 : 0;
-            sm.t_wait += gtimer() - tw0;
-            if (blockIdx.x == FIRST_WORKER) trace_event(p, w, TR_W_ANGLE);
-        }
-        alive = __shfl_sync(0xffffffffu, alive, 0);
-        acc = __shfl_sync(0xffffffffu, acc, 0);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        s = __shfl_sync(0xffffffffu, s, 0);
     }
-    __syncwarp();
-    // E = [i, j] (if rotated) + the orbitals of D other than i, j, in the order of D
-    const bool isI = has && acc && Dq == i, isJ = has && acc && Dq == j, other = has && !isI && !isJ;
+    // E if the rotation is accepted: [i, j] + the orbitals of D other than i, j, in the order of D; if it is not: D itself
+    const bool isI = has && w >= 0 && Dq == i, isJ = has && w >= 0 && Dq == j, other = has && !isI && !isJ;
     const unsigned om = __ballot_sync(0xffffffffu, other);
-    const int base = acc ? 2 : 0;
-    const int tpos = isI ? 0 : (isJ ? 1 : base + __popc(om & ((1u << lane) - 1u)));
-    const int e = base + __popc(om);
-    if (has) {
-        st.D[lane] = Dq;
-        st.tpos[lane] = tpos;
-        if (other) st.E[tpos] = Dq;
-    }
-    if (lane == 0) {
-        st.alive = alive;
-        st.rotated = acc;
-        st.i = i;
-        st.j = j;
-        st.c = c;
-        st.s = s;
-        st.m = m;
-        st.slot = slot;
-        st.e = e;
-        st.nnew = nnew;
-        st.na_before = na_before;
-        sm.na_act = na_before + nnew;
-        if (acc) {
-            st.E[0] = i;
-            st.E[1] = j;
+    const int tpos_acc = isI ? 0 : (isJ ? 1 : 2 + __popc(om & ((1u << lane) - 1u)));
+    const int e_acc = 2 + __popc(om);
+    __syncwarp();
+    // skip mask / row list of the flat phase (accepted case: the tile holds i, j and D)
+    if (w >= 0) {
+        if (has) atomicOr(&skipmask[Dq >> 5], 1u << (Dq & 31));
+        if (lane == 0) {
+            atomicOr(&skipmask[i >> 5], 1u << (i & 31));
+            atomicOr(&skipmask[j >> 5], 1u << (j & 31));
         }
-    }
-    __syncwarp();
-    const int myE = lane < e ? st.E[lane] : -1;
-    if (myE >= 0) atomicOr(&skipmask[myE >> 5], 1u << (myE & 31));
-    __syncwarp();
-    // the rows the flat phase visits: active orbitals outside the tile, ascending (lane <-> one 32-bit word)
-    {
+        __syncwarp();
         const int lo = 32 * lane, nn = p.n;
         const unsigned valid = lo + 32 <= nn ? ~0u : (lo < nn ? ((1u << (nn - lo)) - 1u) : 0u);
         unsigned bits = ~skipmask[lane] & valid;
@@ -834,6 +802,48 @@ __device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm
             fl[pos++] = (short)(lo + b);
         }
         if (lane == 0) sm.nflat[buf] = total;
+    } else if (lane == 0) {
+        sm.nflat[buf] = 0;
+    }
+    if (has) st.D[lane] = Dq;
+    if (lane == 0) {
+        st.i = i;
+        st.j = j;
+        st.m = m;
+        st.slot = slot;
+        st.nnew = nnew;
+        st.na_before = na_before;
+        sm.na_act = na_before + nnew;
+    }
+    // ---- the angle -------------------------------------------------------------------------------------------------
+    int acc = 0, alive = 1;
+    double c = 1.0, s = 0.0;
+    if (w >= 0) {
+        if (lane == 0) {
+            const unsigned long long tw0 = gtimer();
+            alive = read_record(p, w, acc, c, s) ? 1 : 0;
+            sm.t_wait += gtimer() - tw0;
+            if (blockIdx.x == FIRST_WORKER) trace_event(p, w, TR_W_ANGLE);
+        }
+        alive = __shfl_sync(0xffffffffu, alive, 0);
+        acc = __shfl_sync(0xffffffffu, acc, 0);
+    }
+    // what depends on it: the layout of the tile
+    const int tpos = acc ? tpos_acc : lane;
+    if (has) {
+        st.tpos[lane] = tpos;
+        if (!acc || other) st.E[tpos] = Dq;
+    }
+    if (lane == 0) {
+        st.alive = alive;
+        st.rotated = acc;
+        st.c = c;
+        st.s = s;
+        st.e = acc ? e_acc : m;
+        if (acc) {
+            st.E[0] = i;
+            st.E[1] = j;
+        }
     }
 }
 
@@ -937,7 +947,12 @@ __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, dou
 // CTAs 1..NRED: reduction of the partial super blocks (fixed order), publication of the total.  Reducer r owns the
 // entries [ne r / NRED, ne (r + 1) / NRED).
 // =====================================================================================================================
-__device__ __forceinline__ void reducer_main(const Params &p, double *scratch /* [8][SB_MAX] smem */, int *flag_sm, int ridx) {
+#ifdef S3_ROLE_NOINLINE
+#define S3_ROLE static __device__ __noinline__
+#else
+#define S3_ROLE __device__ __forceinline__
+#endif
+S3_ROLE void reducer_main(const Params &p, double *scratch /* [8][SB_MAX] smem */, int *flag_sm, int ridx) {
     const int tid = threadIdx.x;
     unsigned long long t_wait = 0, t_red = 0, tq = gtimer();
     if (tid == 0) flag_sm[0] = 0;
@@ -949,7 +964,10 @@ __device__ __forceinline__ void reducer_main(const Params &p, double *scratch /*
         // `ns` sub-sums per entry over interleaved subsets of the workers: every thread has RLD tagged loads in flight and
         // re-polls a batch until all its tags are those of super block k (with 142 workers and ns = 8 the whole column of an
         // entry is two round trips through L2)
-        constexpr int RLD = 12;
+#ifndef S3_RLD
+#define S3_RLD 12
+#endif
+        constexpr int RLD = S3_RLD;
         const int ns = nl > 0 ? max(1, min(8, THREADS / nl)) : 1;
         const unsigned want = (unsigned)(k + 1);
         const unsigned long long *pb = p.pbuf + (size_t)slot * p.nworkers * SB_MAX * 2;
@@ -974,12 +992,21 @@ __device__ __forceinline__ void reducer_main(const Params &p, double *scratch /*
 #pragma unroll
                 for (int u = 0; u < RLD; ++u) a8[u] += __longlong_as_double((long long)v[u]);
             }
-            // fixed summation tree (independent of arrival order): 12 -> 6 -> 3 -> 1
+            // fixed summation tree (independent of arrival order)
+            static_assert(RLD == 12 || RLD == 8, "reducer: 8 or 12 loads in flight");
+            if (RLD == 12) {
 #pragma unroll
-            for (int u = 0; u < 6; ++u) a8[u] += a8[u + 6];
+                for (int u = 0; u < 6; ++u) a8[u] += a8[u + 6];
 #pragma unroll
-            for (int u = 0; u < 3; ++u) a8[u] += a8[u + 3];
-            scratch[sub * SB_MAX + el] = (a8[0] + a8[1]) + a8[2];
+                for (int u = 0; u < 3; ++u) a8[u] += a8[u + 3];
+                scratch[sub * SB_MAX + el] = (a8[0] + a8[1]) + a8[2];
+            } else {
+#pragma unroll
+                for (int w = 4; w > 0; w >>= 1)
+#pragma unroll
+                    for (int u = 0; u < w; ++u) a8[u] += a8[u + w];
+                scratch[sub * SB_MAX + el] = a8[0];
+            }
         }
         if (!ok) flag_sm[0] = -1;
         __syncthreads();
@@ -1023,7 +1050,7 @@ __device__ __forceinline__ void reducer_main(const Params &p, double *scratch /*
 // =====================================================================================================================
 // CTA NRED + 1: gamma, U, W (global) and the gamma part of the super blocks
 // =====================================================================================================================
-__device__ __forceinline__ void aux_main(const Params &p, int *flag_sm, double *cs_sm) {
+S3_ROLE void aux_main(const Params &p, int *flag_sm, double *cs_sm) {
     const int tid = threadIdx.x, n = p.n;
     const size_t ld = 2 * (size_t)n;
     auto publish_gamma = [&](int k) {       // gamma entries of super block k from the current gamma
@@ -1120,7 +1147,7 @@ struct SearchSmem {
 //     P'[y1,y2,y3,y4] = sum_{pqrs} G0[Y_1,p] G0[Y_2,q] G0[Y_3,r] G0[Y_4,s] P_k[p,q,r,s],   Y = orbitals of pairs k-1 and k (<= 4),
 // G0 = rotation k-2 in the orbitals D_k (rows of i_{k-2}, j_{k-2} have two non-zeros, every other row is a unit vector), as four
 // single-index passes; likewise for the gamma part.  The search threads are left with rotation k-1 on <= 4^4 numbers.
-__device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
+S3_ROLE void fetch_main(const Params &p, SearchSmem &sm) {
     const int ft = threadIdx.x - SEARCH_THREADS;
     for (int k = 0; k < p.P; ++k) {
         const int b = k & 1;
@@ -1130,6 +1157,7 @@ __device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
         const int ne = m_k * m_k * m_k * m_k, ng = 2 * m_k * m_k;
         const int pos_i = dt[7], pos_j = dt[8], pa0 = dt[9], pb0 = dt[10], pa1 = dt[11], pb1 = dt[12];
         bool ok = true;
+#ifndef S3_NO_FETCH_BATCH
         if (p.nranks == 1) {
             // one rank: every word this thread is responsible for (<= 8) is polled in the same round trip
             constexpr int FMAX = (TOT_WORDS + FETCH_THREADS - 1) / FETCH_THREADS;
@@ -1150,6 +1178,7 @@ __device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
                 if (e < ne + ng) sm.sb[e >= ne ? SB_MAX + (e - ne) : e] = __longlong_as_double((long long)v[u]);
             }
         } else
+#endif
         for (int e = ft; e < ne + ng; e += FETCH_THREADS) {
             const bool is_g = e >= ne;
             const int word = is_g ? SB_MAX + (e - ne) : e;
@@ -1297,7 +1326,7 @@ __device__ __forceinline__ void fetch_main(const Params &p, SearchSmem &sm) {
     }
 }
 
-__device__ __forceinline__ void search_main(const Params &p, SearchSmem &sm) {
+S3_ROLE void search_main(const Params &p, SearchSmem &sm) {
     const int tid = threadIdx.x;
     ThetaTablesDev tab = p.tab;
     if (tab.n_coarse <= 320) {
