@@ -964,8 +964,10 @@ S3_ROLE void reducer_main(const Params &p, double *scratch /* [8][SB_MAX] smem *
         // `ns` sub-sums per entry over interleaved subsets of the workers: every thread has RLD tagged loads in flight and
         // re-polls a batch until all its tags are those of super block k (with 142 workers and ns = 8 the whole column of an
         // entry is two round trips through L2)
+        // (12 in flight -- two round trips instead of three with 142 workers -- measured SLOWER end to end: the extra registers
+        // cost the worker paths of the same kernel more than the reducers gain; profiles/r2_final_summary.md)
 #ifndef S3_RLD
-#define S3_RLD 12
+#define S3_RLD 8
 #endif
         constexpr int RLD = S3_RLD;
         const int ns = nl > 0 ? max(1, min(8, THREADS / nl)) : 1;
@@ -1119,12 +1121,10 @@ S3_ROLE void aux_main(const Params &p, int *flag_sm, double *cs_sm) {
 // =====================================================================================================================
 constexpr int MAXY = 4;                              // orbitals of pairs k-1 and k: what is left after the fetch warps' contraction
 constexpr int SBP_WORDS = MAXY * MAXY * MAXY * MAXY + 2 * MAXY * MAXY;   // reduced super block + its gamma part
-constexpr int Z_WORDS = MAXM * MAXM * MAXM * MAXY;   // largest intermediate of the fetch warps' contraction
 
 struct SearchSmem {
     LineSearchSmemT<SEARCH_THREADS> ls;
     double sb[TOT_WORDS];           // super block (+ gamma part) being fetched; consumed by the fetch warps themselves
-    double z[2][Z_WORDS];           // their contraction scratch (ping-pong)
     double sbp[2][SBP_WORDS];       // double-buffered REDUCED super block of the pair being / to be searched: rotation k-2 applied,
                                     // restricted to the <= 4 orbitals Y of pairs k-1 and k: [y1][y2][y3][y4] (stride 4), then gamma [spin][y][y']
     int sb_ok[2];
@@ -1156,8 +1156,9 @@ S3_ROLE void fetch_main(const Params &p, SearchSmem &sm) {
         const int m_k = dt[0];
         const int ne = m_k * m_k * m_k * m_k, ng = 2 * m_k * m_k;
         const int pos_i = dt[7], pos_j = dt[8], pa0 = dt[9], pb0 = dt[10], pa1 = dt[11], pb1 = dt[12];
+        const int in_i = dt[13], in_j = dt[14];       // (loaded here, not after the contraction: an L2 round trip on the chain otherwise)
         bool ok = true;
-#ifndef S3_NO_FETCH_BATCH
+#ifdef S3_FETCH_BATCH       // (all words of a thread in one round trip: measured slower, same reason as S3_RLD = 12)
         if (p.nranks == 1) {
             // one rank: every word this thread is responsible for (<= 8) is polled in the same round trip
             constexpr int FMAX = (TOT_WORDS + FETCH_THREADS - 1) / FETCH_THREADS;
@@ -1246,68 +1247,50 @@ S3_ROLE void fetch_main(const Params &p, SearchSmem &sm) {
                 else if (acc0 && pa0 >= 0 && pos == pb0) { pA = pa0; cA = -s0; pB = pb0; cB = c0; }
                 else { pA = pos; cA = 1.0; pB = pos; cB = 0.0; }
             };
-            const int m = m_k, n1 = nY, n2 = nY * nY, n3 = n2 * nY;
-            // Each pass: one thread per output column (everything but the new index), looping over the new index y, so that
-            // the index arithmetic is one division per thread and pass instead of one per output.
-            // pass 1 (index s): z0[pqr][y4]; the gamma part alongside: sbp[256 + spin*16 + y*4 + y']
-            for (int pqr = ft; pqr < m * m * m; pqr += FETCH_THREADS) {
-                const double *src = sm.sb + pqr * m;
-                for (int y4 = 0; y4 < n1; ++y4) {
-                    int pA, pB;
-                    double cA, cB;
-                    g0row(y4, pA, cA, pB, cB);
-                    sm.z[0][pqr * n1 + y4] = cA * src[pA] + cB * src[pB];
-                }
-            }
-            for (int o = ft; o < 2 * n2; o += FETCH_THREADS) {
-                const int spin = o / n2, r = o - spin * n2, y = r / n1, yy = r - y * n1;
-                int pA, pB, qA, qB;
-                double cA, cB, dA, dB;
-                g0row(y, pA, cA, pB, cB);
-                g0row(yy, qA, dA, qB, dB);
-                const double *gm = sm.sb + SB_MAX + spin * m * m;
-                sm.sbp[b][MAXY * MAXY * MAXY * MAXY + spin * MAXY * MAXY + y * MAXY + yy] =
-                    cA * (dA * gm[pA * m + qA] + dB * gm[pA * m + qB]) + cB * (dA * gm[pB * m + qA] + dB * gm[pB * m + qB]);
-            }
-            named_sync<6, FETCH_THREADS>();
-            // pass 2 (index r): z1[pq][y3][y4]; thread <-> (pq, y4)
-            for (int t = ft; t < m * m * n1; t += FETCH_THREADS) {
-                const int pq = t / n1, y4 = t - pq * n1;
-                for (int y3 = 0; y3 < n1; ++y3) {
-                    int pA, pB;
-                    double cA, cB;
-                    g0row(y3, pA, cA, pB, cB);
-                    sm.z[1][pq * n2 + y3 * n1 + y4] = cA * sm.z[0][(pq * m + pA) * n1 + y4] + cB * sm.z[0][(pq * m + pB) * n1 + y4];
-                }
-            }
-            named_sync<6, FETCH_THREADS>();
-            // pass 3 (index q): z0[p][y2][y3 y4]; thread <-> (p, y3 y4)
-            for (int t = ft; t < m * n2; t += FETCH_THREADS) {
-                const int pp = t / n2, rest = t - pp * n2;
-                for (int y2 = 0; y2 < n1; ++y2) {
-                    int pA, pB;
-                    double cA, cB;
-                    g0row(y2, pA, cA, pB, cB);
-                    sm.z[0][pp * n3 + y2 * n2 + rest] = cA * sm.z[1][(pp * m + pA) * n2 + rest] + cB * sm.z[1][(pp * m + pB) * n2 + rest];
-                }
-            }
-            named_sync<6, FETCH_THREADS>();
-            // pass 4 (index p): sbp[y1][y2][y3][y4] with stride MAXY; thread <-> (y2, y3, y4)
-            for (int r = ft; r < n3; r += FETCH_THREADS) {
-                const int y2 = r / n2, r2 = r - y2 * n2, y3 = r2 / n1, y4 = r2 - y3 * n1;
-                for (int y1 = 0; y1 < n1; ++y1) {
-                    int pA, pB;
-                    double cA, cB;
-                    g0row(y1, pA, cA, pB, cB);
-                    sm.sbp[b][((y1 * MAXY + y2) * MAXY + y3) * MAXY + y4] = cA * sm.z[0][pA * n3 + r] + cB * sm.z[0][pB * n3 + r];
+            // ONE pass: every output P'[y1,y2,y3,y4] is the sum of <= 16 products c1 c2 c3 c4 P[p1,p2,p3,p4] over the (at most two)
+            // non-zeros of the four rows of G0 -- in a run of pairs only the rows of the shared orbital have two, so most
+            // outputs are one or two terms.  (Four single-index passes with a barrier each took 2.7 us next to the busy
+            // search warps and sat on the dependency chain of the sharded runs.)
+            const int m = m_k, n1 = nY, n2 = nY * nY, n3 = n2 * nY, m2 = m * m, m3 = m2 * m;
+            for (int o = ft; o < n1 * n3 + 2 * n2; o += FETCH_THREADS) {
+                if (o < n1 * n3) {
+                    const int y1 = o / n3, r1 = o - y1 * n3, y2 = r1 / n2, r2 = r1 - y2 * n2, y3 = r2 / n1, y4 = r2 - y3 * n1;
+                    int pA[4], pB[4];
+                    double cA[4], cB[4];
+                    g0row(y1, pA[0], cA[0], pB[0], cB[0]);
+                    g0row(y2, pA[1], cA[1], pB[1], cB[1]);
+                    g0row(y3, pA[2], cA[2], pB[2], cB[2]);
+                    g0row(y4, pA[3], cA[3], pB[3], cB[3]);
+                    double acc = 0.0;
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const double c1 = (t & 8) ? cB[0] : cA[0], c2 = (t & 4) ? cB[1] : cA[1], c3 = (t & 2) ? cB[2] : cA[2],
+                                     c4 = (t & 1) ? cB[3] : cA[3];
+                        const double cf = (c1 * c2) * (c3 * c4);
+                        if (cf != 0.0) {
+                            const int q1 = (t & 8) ? pB[0] : pA[0], q2 = (t & 4) ? pB[1] : pA[1], q3 = (t & 2) ? pB[2] : pA[2],
+                                      q4 = (t & 1) ? pB[3] : pA[3];
+                            acc += cf * sm.sb[q1 * m3 + q2 * m2 + q3 * m + q4];
+                        }
+                    }
+                    sm.sbp[b][((y1 * MAXY + y2) * MAXY + y3) * MAXY + y4] = acc;
+                } else {
+                    const int og = o - n1 * n3, spin = og / n2, r = og - spin * n2, y = r / n1, yy = r - y * n1;
+                    int pA, pB, qA, qB;
+                    double cA, cB, dA, dB;
+                    g0row(y, pA, cA, pB, cB);
+                    g0row(yy, qA, dA, qB, dB);
+                    const double *gm = sm.sb + SB_MAX + spin * m2;
+                    sm.sbp[b][MAXY * MAXY * MAXY * MAXY + spin * MAXY * MAXY + y * MAXY + yy] =
+                        cA * (dA * gm[pA * m + qA] + dB * gm[pA * m + qB]) + cB * (dA * gm[pB * m + qA] + dB * gm[pB * m + qB]);
                 }
             }
             if (ft == 0) {
                 int *mt = sm.meta[b];
                 mt[0] = yidx(pos_i);
                 mt[1] = yidx(pos_j);
-                mt[2] = dt[13];
-                mt[3] = dt[14];
+                mt[2] = in_i;
+                mt[3] = in_j;
                 mt[4] = pa1 >= 0 ? yidx(pa1) : -1;
                 mt[5] = pb1 >= 0 ? yidx(pb1) : -1;
             }
