@@ -640,7 +640,7 @@ def chain_table(trace):
     out['pairs_traced'] = len(rows)
     # the raw stamps of the first 12 traced pairs, us since the first one (columns: TR_* 0..9 of csrc/sweep3.cu)
     t0 = tr[tr > 0].min() if (tr > 0).any() else 0.0
-    out['raw_us'] = [[round((v - t0) / 1e3, 2) if v > 0 else None for v in row[:10]] for row in tr[:12]]
+    out['raw_us'] = [[round((v - t0) / 1e3, 2) if v > 0 else None for v in row[:13]] for row in tr[:12]]
     return out
 
 

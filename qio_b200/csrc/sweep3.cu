@@ -121,7 +121,10 @@ enum { TR_SEARCH_START = 0,   // search CTA: super block k is there, contraction
        TR_R_PUB = 6,          // reducer 0: total of super block k published
        TR_F_GOT = 7,          // prefetch warps: total(s) of super block k seen
        TR_F_DONE = 8,         // prefetch warps: reduced super block k ready (full barrier arrives)
-       TR_W_END = 9 };        // worker 0: step k done
+       TR_W_END = 9,          // worker 0: step k done
+       TR_F_PASS = 10,        // prefetch warps, thread 0 (the output with the most terms): its part of the contraction done
+       TR_F_META = 11,        // ... meta data written
+       TR_F_LAST = 12 };      // prefetch warps, last thread (no output of its own): arrives at the closing barrier
 template <typename P_>
 __device__ __forceinline__ void trace_event(const P_ &p, int k, int ev) {
 #ifdef QIO_S3_TIMED
@@ -1255,22 +1258,30 @@ S3_ROLE void fetch_main(const Params &p, SearchSmem &sm) {
             for (int o = ft; o < n1 * n3 + 2 * n2; o += FETCH_THREADS) {
                 if (o < n1 * n3) {
                     const int y1 = o / n3, r1 = o - y1 * n3, y2 = r1 / n2, r2 = r1 - y2 * n2, y3 = r2 / n1, y4 = r2 - y3 * n1;
-                    int pA[4], pB[4];
-                    double cA[4], cB[4];
-                    g0row(y1, pA[0], cA[0], pB[0], cB[0]);
-                    g0row(y2, pA[1], cA[1], pB[1], cB[1]);
-                    g0row(y3, pA[2], cA[2], pB[2], cB[2]);
-                    g0row(y4, pA[3], cA[3], pB[3], cB[3]);
+                    int pA0, pB0, pA1, pB1, pA2, pB2, pA3, pB3;
+                    double cA0, cB0, cA1, cB1, cA2, cB2, cA3, cB3;
+                    g0row(y1, pA0, cA0, pB0, cB0);
+                    g0row(y2, pA1, cA1, pB1, cB1);
+                    g0row(y3, pA2, cA2, pB2, cB2);
+                    g0row(y4, pA3, cA3, pB3, cB3);
+                    // a unit row contributes one term, a rotated row two: the loops run over the non-zero terms only (one or two
+                    // iterations in total for most outputs), in a fixed order.  (The trace shows the heaviest output -- all four
+                    // indices on the shared orbital of a run, 16 terms -- taking 2 us: its ~64 FP64 instructions queue behind
+                    // the search warps on the FP64 pipe of this SM; the other threads finish in 0.5 us.)
+                    const int t0 = cB0 != 0.0 ? 2 : 1, t1 = cB1 != 0.0 ? 2 : 1, t2 = cB2 != 0.0 ? 2 : 1, t3 = cB3 != 0.0 ? 2 : 1;
                     double acc = 0.0;
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) {
-                        const double c1 = (t & 8) ? cB[0] : cA[0], c2 = (t & 4) ? cB[1] : cA[1], c3 = (t & 2) ? cB[2] : cA[2],
-                                     c4 = (t & 1) ? cB[3] : cA[3];
-                        const double cf = (c1 * c2) * (c3 * c4);
-                        if (cf != 0.0) {
-                            const int q1 = (t & 8) ? pB[0] : pA[0], q2 = (t & 4) ? pB[1] : pA[1], q3 = (t & 2) ? pB[2] : pA[2],
-                                      q4 = (t & 1) ? pB[3] : pA[3];
-                            acc += cf * sm.sb[q1 * m3 + q2 * m2 + q3 * m + q4];
+                    for (int a = 0; a < t0; ++a) {
+                        const double c1 = a ? cB0 : cA0;
+                        const int q1 = (a ? pB0 : pA0) * m3;
+                        for (int bq = 0; bq < t1; ++bq) {
+                            const double c12 = c1 * (bq ? cB1 : cA1);
+                            const int q2 = q1 + (bq ? pB1 : pA1) * m2;
+                            for (int cq = 0; cq < t2; ++cq) {
+                                const double c123 = c12 * (cq ? cB2 : cA2);
+                                const int q3 = q2 + (cq ? pB2 : pA2) * m;
+                                for (int d = 0; d < t3; ++d)
+                                    acc += (c123 * (d ? cB3 : cA3)) * sm.sb[q3 + (d ? pB3 : pA3)];
+                            }
                         }
                     }
                     sm.sbp[b][((y1 * MAXY + y2) * MAXY + y3) * MAXY + y4] = acc;
@@ -1285,6 +1296,7 @@ S3_ROLE void fetch_main(const Params &p, SearchSmem &sm) {
                         cA * (dA * gm[pA * m + qA] + dB * gm[pA * m + qB]) + cB * (dA * gm[pB * m + qA] + dB * gm[pB * m + qB]);
                 }
             }
+            if (ft == 0) trace_event(p, k, TR_F_PASS);
             if (ft == 0) {
                 int *mt = sm.meta[b];
                 mt[0] = yidx(pos_i);
@@ -1294,6 +1306,8 @@ S3_ROLE void fetch_main(const Params &p, SearchSmem &sm) {
                 mt[4] = pa1 >= 0 ? yidx(pa1) : -1;
                 mt[5] = pb1 >= 0 ? yidx(pb1) : -1;
             }
+            if (ft == 0) trace_event(p, k, TR_F_META);
+            if (ft == FETCH_THREADS - 1) trace_event(p, k, TR_F_LAST);
         }
         named_sync<6, FETCH_THREADS>();
         if (ft == 0) {
@@ -1507,7 +1521,10 @@ size_t sweep3_mailbox_bytes(int nranks) {
 static size_t worker_smem_bytes(int n, int na, int grid, int &nworkers, int &granule, int &wc_cols) {
     using namespace S3_NS;
     if (grid < FIRST_WORKER + 1 || n > MAXN3 || na < 1) return 0;
-    granule = (n % 4 == 0) ? 4 : ((n % 2 == 0) ? 2 : 1);
+#ifndef S3_GRANULE_MAX
+#define S3_GRANULE_MAX 4
+#endif
+    granule = (n % 4 == 0 && S3_GRANULE_MAX >= 4) ? 4 : ((n % 2 == 0) ? 2 : 1);
     const long long qrow = n / granule, Q = (long long)na * qrow;
     nworkers = (int)std::min<long long>(grid - FIRST_WORKER, Q);
     // the longest owned range, and the most pieces it can break into
