@@ -736,6 +736,7 @@ def multi_gpu_leg(args, n, steps, warmup, rank, world, local_rank, peers, detail
     mem_before = torch.cuda.memory_allocated()
 
     def step(dm1_in, dm2_in):
+        state.pop('st', None)       # release the previous step's shard buffers before the new ones are allocated
         st = ShardedRDM.from_solver(dm1_in, dm2_in, n, peers=peers)
         st.rotate_(U0_d)
         dX, ddX, rec_all = st.all_pairs_pass(inact, tabs)

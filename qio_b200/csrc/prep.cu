@@ -47,7 +47,10 @@ constexpr int PT_T = 64;                       // tile edge
 constexpr int PT_CH = 16;                      // doubles per chunk row (128 bytes)
 constexpr int PT_TILE_DOUBLES = PT_T * PT_T;   // 32 KB
 constexpr int PT_STAGES = 3;
-constexpr int PT_PREFETCH = 8;                 // items whose tiles are requested into L2 ahead of the shared-memory stages
+constexpr int PT_PREFETCH = 8;
+#ifndef PT_MAX_N
+#define PT_MAX_N (2 * PT_T)                    // largest n the TMA kernel is used for (see qio_b200_prep_rdm12)
+#endif                 // items whose tiles are requested into L2 ahead of the shared-memory stages
 constexpr int PT_CONSUMERS = 256;
 constexpr int PT_THREADS = PT_CONSUMERS + 64;      // + a loader warp and a storer warp (one thread each)
 
@@ -355,7 +358,7 @@ static int prep_tma_launch(const double *dm2, double *Gamma, int n, int na, cuda
             const cuuint32_t box[4] = {PT_CH, 1, (cuuint32_t)(PT_CH * k), 1};
             const cuuint32_t estr[4] = {1, 1, 1, 1};
             if (encode(&maps.in[k - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double *>(dm2), gdim, gstride, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return 0;
         }
@@ -429,7 +432,7 @@ extern "C" int qio_b200_prep_rdm12(const double *dm1, const double *dm2, double 
         // The TMA kernel wins where a matrix is at most 2 x 2 tiles (n <= 128: 0.40 ms at n = 100 against 0.42); beyond, its
         // stores -- 128-byte row pieces per chunk box, the same rows revisited by up to 13 boxes -- drain at 2.2 TB/s and the
         // cp-style kernel with its 416-byte row pieces is faster (n = 200: 6.6 against 7.3 ms; profiles/r2_prep_summary.md).
-        if (n % 2 == 0 && n >= 16 && n <= 2 * PT_T && (uintptr_t)dm2 % 16 == 0 && (uintptr_t)Gamma % 16 == 0 &&
+        if (n % 2 == 0 && n >= 16 && n <= PT_MAX_N && (uintptr_t)dm2 % 16 == 0 && (uintptr_t)Gamma % 16 == 0 &&
             (long long)na * n < 0x7fffffffLL) {
             const int rc = prep_tma_launch(dm2, Gamma, n, na, st);
             if (rc != 0) return rc < 0 ? rc : QIO_B200_OK;
