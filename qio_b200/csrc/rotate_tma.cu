@@ -17,8 +17,8 @@
 //   * B (the rotation matrix, <= 104 columns per CTA) is resident in shared memory for the whole kernel, k-major with a
 //     pitch = 2 mod 16 doubles (conflict-free for the same k-groups);
 //   * the N tiles are split 7 + 6 between the two warp columns (warps w and w + 4 share a scheduler), so that n = 100 is
-//     padded to 104 columns instead of 112; when K = 4 mod 8 (n = 100, 28, ...) the last slab runs ONE k-group over its four
-//     valid rows instead of two half-empty ones (K is not padded to 104 either);
+//     padded to 104 columns instead of 112 (skipping the empty half of the last K slab when K = 4 mod 8 was tried and
+//     dropped: the run-time test in the unrolled k-group loop cost 4-7 %, more than the 4 % of the tensor work it saved);
 //   * batched: `batch` independent problems of the same shape (the slabs of a leading-index shard, qio_b200_rotate_axis_batched)
 //     are one launch -- the tensor map has the batch as its fourth dimension and the persistent tile loop runs over
 //     (batch, M tile).
@@ -29,10 +29,14 @@ namespace qio {
 constexpr int RT_BM = 128;            // rows of an M tile
 constexpr int RT_KS = 8;              // k-rows per stage
 constexpr int RT_STAGE_DOUBLES = RT_KS * RT_BM;      // 8 KB
-constexpr int RT_CONSUMERS = 256;     // 8 warps: 4 (M) x 2 (N)
+constexpr int RT_NCOL = 2;            // warp columns (N direction).  Three columns (12 warps, 5 + 4 + 4 tiles, three warps per
+                                      // scheduler against the "wait" stalls of the DMMA chain) measured +1 % at n = 100 and -5 % at
+                                      // n = 200: not kept (profiles/r2_final_summary.md)
+constexpr int RT_CONSUMERS = 128 * RT_NCOL;     // 8 warps: 4 (M) x 2 (N)
 constexpr int RT_THREADS = RT_CONSUMERS + 32;
-constexpr int RT_MAX_NT = 7;          // n8-tiles of the wider warp column
-constexpr int RT_MAX_COLS = 8 * (2 * RT_MAX_NT - 1);   // 104 columns per CTA
+constexpr int RT_MAX_NT = 7;          // n8-tiles of the widest warp column
+constexpr int RT_MAX_TILES = 13;      // n8-tiles per CTA: 7 + 6
+constexpr int RT_MAX_COLS = 8 * RT_MAX_TILES;          // 104 columns per CTA
 constexpr int RT_MAX_STAGES = 8;
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -58,7 +62,6 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
     const int n0 = blockIdx.y * cols_per_cta, ncols = min(cols_per_cta, n - n0);
     const int nslabs = kpad / RT_KS;
     const long long mtiles_b = (rows + RT_BM - 1) / RT_BM, mtiles = mtiles_b * batch;
-    const bool half_last = (kdim & 7) == 4;     // the last slab holds four valid k-rows: one k-group instead of two
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -93,8 +96,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
     // ---- consumers: 8 warps as 4 (M) x 2 (N) -------------------------------------------------------------------
     const int g = lane >> 2, t = lane & 3;
     const int wm = (warp & 3) * 32, wcol = warp >> 2;
-    const int tiles_n = (ncols + 7) / 8, nt_a = (tiles_n + 1) / 2;           // column 0: nt_a tiles, column 1: the rest
-    const int nt = wcol == 0 ? nt_a : tiles_n - nt_a, wn = wcol == 0 ? 0 : 8 * nt_a;
+    // the n8-tiles are dealt to the warp columns as evenly as possible (13 -> 7 + 6), the wider ones first
+    const int tiles_n = (ncols + 7) / 8;
+    const int nt = (tiles_n + RT_NCOL - 1 - wcol) / RT_NCOL;
+    int wn = 0;
+    for (int c = 0; c < wcol; ++c) wn += 8 * ((tiles_n + RT_NCOL - 1 - c) / RT_NCOL);
     // per-lane constants of the swizzled A fragment: m = wm + 8 mi + g -> 16-double line chunk and position inside
     int a_line[4], a_unit[4], a_low[4];
 #pragma unroll
@@ -116,11 +122,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
             mbar_wait(full + s, (unsigned)((q / stages) & 1));
             const double *a = sA + (size_t)s * RT_STAGE_DOUBLES;
             const double *b = sB + (size_t)(ks * RT_KS) * np + wn + g;
-            const bool half = half_last && ks == nslabs - 1;
 #pragma unroll
             for (int grp = 0; grp < 2; ++grp) {
-                if (half && grp == 1) break;
-                const int r = half ? t : 2 * t + grp;   // k-group: rows {0, 2, 4, 6} (+1) of the slab; {0, 1, 2, 3} of a half slab
+                const int r = 2 * t + grp;          // k-group: rows {0, 2, 4, 6} (+1) of the slab
                 double af[4], bf[RT_MAX_NT];
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi)
