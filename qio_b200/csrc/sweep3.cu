@@ -99,6 +99,7 @@ struct Params {
     const int32_t *dtab;        // [P][DT_STRIDE] per-pair table (see build_dtab_kernel)
     int nworkers;               // workers that own at least one column
     int granule;                // doubles per ownership quantum (4, 2 or 1)
+    int flat_unr;               // butterflies in flight per thread in the flat phase (3 or 4)
     int wc_cols;                // row pitch of a worker's private W columns
     double *wg;                 // [nworkers][n][wc_cols] every worker's own columns of W (global, L2-resident, private)
     double *rg;                 // [nworkers][n][n] every worker's copy of the rotation accumulated in this launch, in
@@ -317,11 +318,10 @@ __device__ __forceinline__ int piece_of(const WorkerSmem &sm, int cc) {
 // `flatlist` (active orbitals outside the tile), strided over `nt` threads (this one is number t): rows (i, x), (j, x)
 // (axis 0) or (x, i), (x, j) (axis 1) rotated by (c, s).  A separate function on purpose: its loop wants a clean register file
 // (four butterflies = eight independent 16-byte loads in flight per thread).
-template <int V>
+template <int V, int UNR>
 static __device__ __noinline__ void flat_update(double *__restrict__ S, const WorkerSmem *smp, const short *flatlist, int nflat, int n,
                                                 int i, int j, double c, double s, int t, int nt) {
     using VT = typename std::conditional<V == 2, double2, double>::type;
-    constexpr int UNR = 4;
     const WorkerSmem &sm = *smp;
     const long long n1 = n, n2 = n1 * n1;
     const int lv = sm.ncd / V;
@@ -732,7 +732,12 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
     }
 
     // ---- flat phase: every other row pair of rotation (i, j) inside the owned columns ----------------------------
-    if (rot) flat_update<V>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, tid, WORK_THREADS);
+    // butterflies in flight per thread: three where the rows of one rotation stay in L2, four where they stream from DRAM
+    // (measured: n = 100 47.5 / 48.5 ms per cycle with 3 / 4, n = 200 1284 / 1228 ms; two or five are slower at both sizes)
+    if (rot) {
+        if (p.flat_unr == 3) flat_update<V, 3>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, tid, WORK_THREADS);
+        else flat_update<V, 4>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, tid, WORK_THREADS);
+    }
     if (tm2) sm.t_flat += gtimer() - t_b2;
     if (widx == 0 && tid == 0) trace_event(p, st.slot - LOOK, TR_W_END);
 }
@@ -1584,6 +1589,7 @@ int S3_LAUNCH(double *gamma, double *S, double *U, double *W, int n, int a0, int
     p.pbuf = reinterpret_cast<unsigned long long *>(ws + L.off_pbuf);
     p.timeout_ns = 1000000ull * (opts.timeout_ms ? opts.timeout_ms : 4000u);
     p.startup_timeout_ns = 1000000ull * (opts.startup_timeout_ms ? opts.startup_timeout_ms : 60000u);
+    p.flat_unr = (32.0 * (double)n * n * na < 48e6) ? 3 : 4;      // bytes one rotation reads on this rank vs what stays in L2
     p.blocks_out = opts.blocks_out;
     p.trace = opts.trace_out;
     p.trace_k0 = opts.trace_first_pair;
