@@ -1144,6 +1144,7 @@ struct SearchSmem {
     // angle history for the fetch warps: written by search thread 0 the moment pair k is decided
     int hist_acc[4];
     double hist_c[4], hist_s[4];
+    double ctab[2][25];             // c^x s^y (x + 5 y) of the rotation the prefetch warps apply, per buffer
     int decided;                    // last decided pair (-1 at start); volatile accesses
     int fetch_abort;
 };
@@ -1227,6 +1228,14 @@ S3_ROLE void fetch_main(const Params &p, SearchSmem &sm) {
             c0 = sm.hist_c[(k - 2) & 3];
             s0 = sm.hist_s[(k - 2) & 3];
         }
+        // every coefficient of the contraction below is +- c0^x s0^y with x + y <= 4: 25 numbers, one thread each
+        if (ft < 25) {
+            const int x = ft % 5, y = ft / 5;
+            double v = 1.0;
+            for (int q = 0; q < x; ++q) v *= c0;
+            for (int q = 0; q < y; ++q) v *= s0;
+            sm.ctab[b][ft] = v;
+        }
         if (!ok) sm.fetch_abort = 1;
         if (k == 0 && ft == 0 && ok) atomicExch(p.abort_flag + 1, 1u);      // start-up is over: the normal time-out applies
         named_sync<6, FETCH_THREADS>();
@@ -1263,30 +1272,38 @@ S3_ROLE void fetch_main(const Params &p, SearchSmem &sm) {
             for (int o = ft; o < n1 * n3 + 2 * n2; o += FETCH_THREADS) {
                 if (o < n1 * n3) {
                     const int y1 = o / n3, r1 = o - y1 * n3, y2 = r1 / n2, r2 = r1 - y2 * n2, y3 = r2 / n1, y4 = r2 - y3 * n1;
-                    int pA0, pB0, pA1, pB1, pA2, pB2, pA3, pB3;
-                    double cA0, cB0, cA1, cB1, cA2, cB2, cA3, cB3;
-                    g0row(y1, pA0, cA0, pB0, cB0);
-                    g0row(y2, pA1, cA1, pB1, cB1);
-                    g0row(y3, pA2, cA2, pB2, cB2);
-                    g0row(y4, pA3, cA3, pB3, cB3);
-                    // a unit row contributes one term, a rotated row two: the loops run over the non-zero terms only (one or two
-                    // iterations in total for most outputs), in a fixed order.  (The trace shows the heaviest output -- all four
-                    // indices on the shared orbital of a run, 16 terms -- taking 2 us: its ~64 FP64 instructions queue behind
-                    // the search warps on the FP64 pipe of this SM; the other threads finish in 0.5 us.)
-                    const int t0 = cB0 != 0.0 ? 2 : 1, t1 = cB1 != 0.0 ? 2 : 1, t2 = cB2 != 0.0 ? 2 : 1, t3 = cB3 != 0.0 ? 2 : 1;
+                    // rows in coded form: term A / B = position, exponent code (x + 5 y of c0^x s0^y) and sign; nt = 1 or 2 terms.
+                    // A product of four coefficients is then a table entry (sum of the codes) with a sign: ONE FP64 instruction per
+                    // term instead of four -- the FP64 pipe of this SM belongs to the search warps, and the output with all four
+                    // indices on the shared orbital of a run (16 terms) used to take 2 us on the dependency chain.
+                    auto coded = [&](int y, int &pA, int &eA, int &gA, int &pB, int &eB, int &nt) {
+                        const int pos = y == 0 ? Y0 : (y == 1 ? Y1 : (y == 2 ? Y2 : Y3));
+                        if (acc0 && pa0 >= 0 && pos == pa0) { pA = pa0; eA = 1; gA = 0; pB = pb0; eB = 5; nt = 2; }          // c0 e_a + s0 e_b
+                        else if (acc0 && pa0 >= 0 && pos == pb0) { pA = pa0; eA = 5; gA = 1; pB = pb0; eB = 1; nt = 2; }    // -s0 e_a + c0 e_b
+                        else { pA = pos; eA = 0; gA = 0; pB = pos; eB = 0; nt = 1; }
+                    };
+                    int pA0, eA0, gA0, pB0, eB0, t0, pA1, eA1, gA1, pB1, eB1, t1, pA2, eA2, gA2, pB2, eB2, t2, pA3, eA3, gA3, pB3, eB3, t3;
+                    coded(y1, pA0, eA0, gA0, pB0, eB0, t0);
+                    coded(y2, pA1, eA1, gA1, pB1, eB1, t1);
+                    coded(y3, pA2, eA2, gA2, pB2, eB2, t2);
+                    coded(y4, pA3, eA3, gA3, pB3, eB3, t3);
+                    const double *ct = sm.ctab[b];
                     double acc = 0.0;
                     for (int a = 0; a < t0; ++a) {
-                        const double c1 = a ? cB0 : cA0;
-                        const int q1 = (a ? pB0 : pA0) * m3;
+                        const int e1 = a ? eB0 : eA0, g1 = a ? 0 : gA0, q1 = (a ? pB0 : pA0) * m3;
                         for (int bq = 0; bq < t1; ++bq) {
-                            const double c12 = c1 * (bq ? cB1 : cA1);
-                            const int q2 = q1 + (bq ? pB1 : pA1) * m2;
+                            const int e2 = e1 + (bq ? eB1 : eA1), g2 = g1 ^ (bq ? 0 : gA1), q2 = q1 + (bq ? pB1 : pA1) * m2;
+                            double part = 0.0;
                             for (int cq = 0; cq < t2; ++cq) {
-                                const double c123 = c12 * (cq ? cB2 : cA2);
-                                const int q3 = q2 + (cq ? pB2 : pA2) * m;
-                                for (int d = 0; d < t3; ++d)
-                                    acc += (c123 * (d ? cB3 : cA3)) * sm.sb[q3 + (d ? pB3 : pA3)];
+                                const int e3 = e2 + (cq ? eB2 : eA2), g3 = g2 ^ (cq ? 0 : gA2), q3 = q2 + (cq ? pB2 : pA2) * m;
+                                for (int d = 0; d < t3; ++d) {
+                                    const double cf = ct[e3 + (d ? eB3 : eA3)];
+                                    const int neg = g3 ^ (d ? 0 : gA3);
+                                    const double sgn = __hiloint2double(__double2hiint(cf) ^ (neg << 31), __double2loint(cf));
+                                    part = fma(sgn, sm.sb[q3 + (d ? pB3 : pA3)], part);
+                                }
                             }
+                            acc += part;
                         }
                     }
                     sm.sbp[b][((y1 * MAXY + y2) * MAXY + y3) * MAXY + y4] = acc;
@@ -1312,7 +1329,7 @@ S3_ROLE void fetch_main(const Params &p, SearchSmem &sm) {
                 mt[5] = pb1 >= 0 ? yidx(pb1) : -1;
             }
             if (ft == 0) trace_event(p, k, TR_F_META);
-            if (ft == FETCH_THREADS - 1) trace_event(p, k, TR_F_LAST);
+            if (ft == 80) trace_event(p, k, TR_F_LAST);       // a thread whose output has a single term (all rows unit vectors)
         }
         named_sync<6, FETCH_THREADS>();
         if (ft == 0) {
