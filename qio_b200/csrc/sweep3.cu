@@ -68,7 +68,17 @@ constexpr int TILE_LEN = 96;     // owned columns handled per super-block tile
 constexpr int TILE_PITCH = 98;   // row pitch of the tile: 196 words = 4 mod 32, the 8 rows a warp reads fall on different banks
 constexpr int DT_STRIDE = 16;     // ints per entry of the per-pair table
 constexpr int WORK_THREADS = THREADS - 32;   // a worker's warps 0..14 compute, warp 15 plans the next step (polls the angle)
-constexpr int TILE_THREADS = WORK_THREADS;   // all working warps do the tile phase, then the flat phase
+// The two phases of a worker step touch disjoint rows (the flat phase leaves the rows of the tile alone), so they run
+// CONCURRENTLY on two groups of warps: warps 0..4 the latency-bound tile phase (rows of the next super block: load, rotate,
+// dot products, post), warps 5..14 the bandwidth-bound flat phase (everything else of the rotation).  A step then lasts
+// max(tile, flat) instead of tile + flat.  (Round 1 tried this split and dropped it: with a fixed four butterflies in flight per
+// thread the smaller flat group could not keep enough loads in flight; the flat group now runs five or six.)
+#ifndef S3_TILE_THREADS
+#define S3_TILE_THREADS 160
+#endif
+constexpr int TILE_THREADS = S3_TILE_THREADS;
+constexpr int FLAT_THREADS = WORK_THREADS - TILE_THREADS;
+static_assert(TILE_THREADS % 32 == 0 && TILE_THREADS >= 96 && FLAT_THREADS >= 32, "worker thread groups");
 constexpr int MAXN3 = 1024;      // largest n of the pipelined kernel (rank / activation tables in shared memory)
 constexpr int CU_COLS = 32;       // columns per catch-up chunk (one per lane)
 constexpr int CU_PITCH = 36;      // pitch of the staged catch-up vectors (conflict-free B fragments)
@@ -497,6 +507,20 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
         for (int q = 0; q < st.nnew; ++q) catch_up(p, sm, Rg, cu_in, st.newc[q], st.na_before);
         if (widx == 0 && tid == 0) sm.t_d[2] += gtimer() - tc0;
     }
+    // ---- flat group: every other row pair of rotation (i, j) inside the owned columns, while the tile group works ------
+    if (tid >= TILE_THREADS) {
+        const bool tmf = (widx == 0 && tid == TILE_THREADS);
+        const unsigned long long tf0 = tmf ? gtimer() : 0;
+        if (rot) {
+            const int ft = tid - TILE_THREADS;
+            if (p.flat_unr == 4) flat_update<V, 4>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, FLAT_THREADS);
+            else if (p.flat_unr == 5) flat_update<V, 5>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, FLAT_THREADS);
+            else flat_update<V, 3>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, FLAT_THREADS);
+        }
+        if (tmf) sm.t_flat += gtimer() - tf0;
+        return;
+    }
+    // ---- tile group from here on --------------------------------------------------------------------------------------
     // ---- accumulated rotation: rows rank(i), rank(j) over the active columns (loads here, stores in w_consume)
     const int nact = st.na_before + st.nnew, ri = rot ? sm.rank[i] : 0, rj = rot ? sm.rank[j] : 0;
     double rx = 0.0, ry = 0.0;
@@ -563,61 +587,54 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
 
     // ---- tile phase: the rows (x, y), x, y in E, of all owned columns ------------------------------------------
     // orbits of the rotation inside E x E: X = {IJ} + F (rotated) or X = E (not rotated); an orbit has 1, 2 or 4 rows
-    const int nx = rot ? e - 1 : e;              // size of X
     const int m3 = m * m * m, ndot = sm.npieces * m3;
     const unsigned ptag = (unsigned)(st.slot + 1);
     unsigned long long *pslot = p.pbuf + ((size_t)(st.slot & (SLOTS - 1)) * p.nworkers + widx) * SB_MAX * 2;
+    // All e x e rows of the chunk arrive asynchronously in ONE round trip whatever the number of threads (cp.async, no
+    // registers); the rows the rotation touches are then rotated in shared memory -- the orbit {i, j} x {i, j} (four rows), the
+    // orbits {i, j} x f and f x {i, j} (two rows each), same operation order as ever -- and written back.
     auto tile_pass = [&](int t0, int tl) {
-        const int tv = tl / V, nitems = nx * nx * tv;
-        for (int item = tid; item < nitems; item += TILE_THREADS) {
-            const int orb = item / tv, v = item - orb * tv;
-            const int x1 = orb / nx, x2 = orb - x1 * nx;
-            const bool two1 = rot && x1 == 0, two2 = rot && x2 == 0;
-            const int ea0 = rot ? (x1 == 0 ? 0 : x1 + 1) : x1, eb0 = rot ? (x2 == 0 ? 0 : x2 + 1) : x2;   // E positions
-            const int oa0 = st.E[ea0], ob0 = st.E[eb0];
+        const int tv = tl / V;
+        for (int item = tid; item < e * e * tv; item += TILE_THREADS) {
+            const int rowidx = item / tv, v = item - rowidx * tv, ea = rowidx / e, eb = rowidx - ea * e;
             const int cc = t0 + v * V;
-            double *g = p.S + sm.piece[piece_of(sm, cc)].base + cc + oa0 * n2 + ob0 * n1;
-            if (!two1 && !two2) {
-                // a row the rotation does not touch: only the dot products need it -- copied asynchronously, so that a
-                // thread's blocking (rotated) item and its untouched items share one latency window
-                if (m > 0) {
-                    VT *dst = reinterpret_cast<VT *>(sm.tile + (ea0 * e + eb0) * TILE_PITCH) + v;
-                    if constexpr (V == 2) cp_async_16(dst, g); else cp_async_8(dst, g);
-                }
-                continue;
-            }
-            const long long dj1 = (long long)(j - oa0) * n2, dj2 = (long long)(j - ob0) * n1;   // to the partner rows
-            VT q0, q1, q2, q3;      // rows (a, b), (a, j), (j, b), (j, j)
-            q0 = __ldcg(reinterpret_cast<const VT *>(g));
-            if (two2) q1 = __ldcg(reinterpret_cast<const VT *>(g + dj2));
-            if (two1) q2 = __ldcg(reinterpret_cast<const VT *>(g + dj1));
-            if (two1 && two2) q3 = __ldcg(reinterpret_cast<const VT *>(g + dj1 + dj2));
-            if (two1 && two2) {
+            const double *g = p.S + sm.piece[piece_of(sm, cc)].base + cc + st.E[ea] * n2 + st.E[eb] * n1;
+            VT *dst = reinterpret_cast<VT *>(sm.tile + rowidx * TILE_PITCH) + v;
+            if constexpr (V == 2) cp_async_16(dst, g); else cp_async_8(dst, g);
+        }
+        cp_async_wait_all();
+        named_sync<3, TILE_THREADS>();
+        if (!rot) return;
+        const int norb = 1 + 2 * (e - 2);
+        for (int item = tid; item < norb * tv; item += TILE_THREADS) {
+            const int orb = item / tv, v = item - orb * tv;
+            const int cc = t0 + v * V;
+            double *gbase = p.S + sm.piece[piece_of(sm, cc)].base + cc;
+            auto T = [&](int ea, int eb) { return reinterpret_cast<VT *>(sm.tile + (ea * e + eb) * TILE_PITCH) + v; };
+            auto G = [&](int ea, int eb) { return reinterpret_cast<VT *>(gbase + st.E[ea] * n2 + st.E[eb] * n1); };
+            if (orb == 0) {
+                VT q0 = *T(0, 0), q1 = *T(0, 1), q2 = *T(1, 0), q3 = *T(1, 1);      // rows (i, i), (i, j), (j, i), (j, j)
                 bf(q0, q1);       // axis 2 on row i
                 bf(q2, q3);       // axis 2 on row j
                 bf(q0, q2);       // axis 1 on column i
                 bf(q1, q3);       // axis 1 on column j
-                *reinterpret_cast<VT *>(g) = q0;
-                *reinterpret_cast<VT *>(g + dj2) = q1;
-                *reinterpret_cast<VT *>(g + dj1) = q2;
-                *reinterpret_cast<VT *>(g + dj1 + dj2) = q3;
-            } else if (two1) {
+                *T(0, 0) = q0; *T(0, 1) = q1; *T(1, 0) = q2; *T(1, 1) = q3;
+                *G(0, 0) = q0; *G(0, 1) = q1; *G(1, 0) = q2; *G(1, 1) = q3;
+            } else if (orb <= e - 2) {
+                const int f = orb + 1;                                             // rows (i, f), (j, f): axis 1
+                VT q0 = *T(0, f), q2 = *T(1, f);
                 bf(q0, q2);
-                *reinterpret_cast<VT *>(g) = q0;
-                *reinterpret_cast<VT *>(g + dj1) = q2;
-            } else if (two2) {
+                *T(0, f) = q0; *T(1, f) = q2;
+                *G(0, f) = q0; *G(1, f) = q2;
+            } else {
+                const int f = orb - (e - 2) + 1;                                   // rows (f, i), (f, j): axis 2
+                VT q0 = *T(f, 0), q1 = *T(f, 1);
                 bf(q0, q1);
-                *reinterpret_cast<VT *>(g) = q0;
-                *reinterpret_cast<VT *>(g + dj2) = q1;
-            }
-            if (m > 0) {
-                *(reinterpret_cast<VT *>(sm.tile + (ea0 * e + eb0) * TILE_PITCH) + v) = q0;
-                if (two2) *(reinterpret_cast<VT *>(sm.tile + (ea0 * e + 1) * TILE_PITCH) + v) = q1;
-                if (two1) *(reinterpret_cast<VT *>(sm.tile + (1 * e + eb0) * TILE_PITCH) + v) = q2;
-                if (two1 && two2) *(reinterpret_cast<VT *>(sm.tile + (1 * e + 1) * TILE_PITCH) + v) = q3;
+                *T(f, 0) = q0; *T(f, 1) = q1;
+                *G(f, 0) = q0; *G(f, 1) = q1;
             }
         }
-        cp_async_wait_all();
+        named_sync<3, TILE_THREADS>();
     };
     // dot (piece, q, r, s) over the columns [t0, t0 + tl) of the tile; s varies fastest over the lanes (same tile element:
     // broadcast), the rows a warp reads sit on different banks (TILE_PITCH)
@@ -650,7 +667,7 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
     if (single) {
         tile_pass(0, sm.ncd);
         w_consume();
-        named_sync<2, TILE_THREADS>();
+        named_sync<3, TILE_THREADS>();
         if (tm2) {
             const unsigned long long t = gtimer();
             sm.t_pass += t - t_b2;
@@ -685,7 +702,7 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
                     if (part == 0 && idx < ndot) sm.dots[idx] = acc;
                 }
                 if (tmd) { const unsigned long long t = gtimer(); sm.t_d[1] += t - td; td = t; }
-                named_sync<2, TILE_THREADS>();
+                named_sync<3, TILE_THREADS>();
                 if (tmd) td = gtimer();
                 for (int en = tid; en < M * M3; en += TILE_THREADS) {
                     const int pp = en / M3, qrs = en - pp * M3;
@@ -705,24 +722,27 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
             }
         }
     } else {
-        double dacc[2] = {0.0, 0.0};                 // thread <-> dot (piece, q, r, s) = tid, tid + THREADS
+        constexpr int DACC = (MAX_PIECES * MAXM * MAXM * MAXM + TILE_THREADS - 1) / TILE_THREADS;
+        double dacc[DACC];                           // thread <-> dots (piece, q, r, s) = tid, tid + TILE_THREADS, ...
+#pragma unroll
+        for (int h = 0; h < DACC; ++h) dacc[h] = 0.0;
         for (int t0 = 0; t0 < sm.ncd; t0 += TILE_LEN) {
             const int tl = min(TILE_LEN, sm.ncd - t0);
             tile_pass(t0, tl);
             if (t0 == 0) w_consume();
             if (m > 0) {
-                named_sync<2, TILE_THREADS>();
+                named_sync<3, TILE_THREADS>();
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < DACC; ++h)
                     if (tid + h * TILE_THREADS < ndot) dacc[h] += tile_dot(tid + h * TILE_THREADS, t0, tl);
-                named_sync<2, TILE_THREADS>();        // the tile is overwritten by the next chunk
+                named_sync<3, TILE_THREADS>();        // the tile is overwritten by the next chunk
             }
         }
         if (m > 0) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < DACC; ++h)
                 if (tid + h * TILE_THREADS < ndot) sm.dots[tid + h * TILE_THREADS] = dacc[h];
-            named_sync<2, TILE_THREADS>();
+            named_sync<3, TILE_THREADS>();
             for (int en = tid; en < m * m3; en += TILE_THREADS) post_entry(en);
         }
     }
@@ -731,14 +751,6 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
         trace_event(p, st.slot, TR_W_POSTED);
     }
 
-    // ---- flat phase: every other row pair of rotation (i, j) inside the owned columns ----------------------------
-    // butterflies in flight per thread: three where the rows of one rotation stay in L2, four where they stream from DRAM
-    // (measured: n = 100 47.5 / 48.5 ms per cycle with 3 / 4, n = 200 1284 / 1228 ms; two or five are slower at both sizes)
-    if (rot) {
-        if (p.flat_unr == 3) flat_update<V, 3>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, tid, WORK_THREADS);
-        else flat_update<V, 4>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, tid, WORK_THREADS);
-    }
-    if (tm2) sm.t_flat += gtimer() - t_b2;
     if (widx == 0 && tid == 0) trace_event(p, st.slot - LOOK, TR_W_END);
 }
 
@@ -1606,7 +1618,10 @@ int S3_LAUNCH(double *gamma, double *S, double *U, double *W, int n, int a0, int
     p.pbuf = reinterpret_cast<unsigned long long *>(ws + L.off_pbuf);
     p.timeout_ns = 1000000ull * (opts.timeout_ms ? opts.timeout_ms : 4000u);
     p.startup_timeout_ns = 1000000ull * (opts.startup_timeout_ms ? opts.startup_timeout_ms : 60000u);
-    p.flat_unr = (32.0 * (double)n * n * na < 48e6) ? 3 : 4;      // bytes one rotation reads on this rank vs what stays in L2
+#ifndef S3_FLAT_UNR
+#define S3_FLAT_UNR 5
+#endif
+    p.flat_unr = S3_FLAT_UNR;      // butterflies in flight per thread of the flat group (3, 4 or 5)
     p.blocks_out = opts.blocks_out;
     p.trace = opts.trace_out;
     p.trace_k0 = opts.trace_first_pair;
