@@ -69,12 +69,13 @@ constexpr int TILE_PITCH = 98;   // row pitch of the tile: 196 words = 4 mod 32,
 constexpr int DT_STRIDE = 16;     // ints per entry of the per-pair table
 constexpr int WORK_THREADS = THREADS - 32;   // a worker's warps 0..14 compute, warp 15 plans the next step (polls the angle)
 // The two phases of a worker step touch disjoint rows (the flat phase leaves the rows of the tile alone), so they run
-// CONCURRENTLY on two groups of warps: warps 0..4 the latency-bound tile phase (rows of the next super block: load, rotate,
-// dot products, post), warps 5..14 the bandwidth-bound flat phase (everything else of the rotation).  A step then lasts
+// CONCURRENTLY on two groups of warps: warps 0..3 the latency-bound tile phase (rows of the next super block: load, rotate,
+// dot products, post), the other working warps the bandwidth-bound flat phase (everything else of the rotation).  A step then lasts
 // max(tile, flat) instead of tile + flat.  (Round 1 tried this split and dropped it: with a fixed four butterflies in flight per
-// thread the smaller flat group could not keep enough loads in flight; the flat group now runs five or six.)
+// thread the smaller flat group could not keep enough loads in flight; the flat group now runs five, and the tile group's
+// loads are cp.async, one round trip whatever its size.)
 #ifndef S3_TILE_THREADS
-#define S3_TILE_THREADS 160
+#define S3_TILE_THREADS 128         // measured: 96 / 128 / 160 / 192 tile threads -> 46.3 / 41.3 / 41.6 / 41.6 ms per n = 100 cycle
 #endif
 constexpr int TILE_THREADS = S3_TILE_THREADS;
 constexpr int FLAT_THREADS = WORK_THREADS - TILE_THREADS;
@@ -510,6 +511,8 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
     // ---- flat group: every other row pair of rotation (i, j) inside the owned columns, while the tile group works ------
     if (tid >= TILE_THREADS) {
         const bool tmf = (widx == 0 && tid == TILE_THREADS);
+        // (letting the tile group issue its loads first -- a named barrier here, released after its cp.async loop -- was tried:
+        // 41.1 -> 44.0 ms per n = 100 cycle, the flat group is the longer of the two on one GPU)
         const unsigned long long tf0 = tmf ? gtimer() : 0;
         if (rot) {
             const int ft = tid - TILE_THREADS;
