@@ -74,18 +74,17 @@ constexpr int WORK_THREADS = THREADS - 32;   // a worker's warps 0..14 compute, 
 // max(tile, flat) instead of tile + flat.  (Round 1 tried this split and dropped it: with a fixed four butterflies in flight per
 // thread the smaller flat group could not keep enough loads in flight; the flat group now runs five, and the tile group's
 // loads are cp.async, one round trip whatever its size.)
-#ifndef S3_TILE_THREADS
-#define S3_TILE_THREADS 128         // measured: 96 / 128 / 160 / 192 tile threads -> 46.3 / 41.3 / 41.6 / 41.6 ms per n = 100 cycle
-#endif
-constexpr int TILE_THREADS = S3_TILE_THREADS;
-constexpr int FLAT_THREADS = WORK_THREADS - TILE_THREADS;
-static_assert(TILE_THREADS % 32 == 0 && TILE_THREADS >= 96 && FLAT_THREADS >= 32, "worker thread groups");
+// The split is chosen per launch (Params::tile_threads): 128 tile threads where the flat phase is the longer one (one GPU, n = 100:
+// 96 / 128 / 160 / 192 -> 46.3 / 41.3 / 41.6 / 41.6 ms per cycle), more where a rank's share of the rotation is small and the
+// tile phase sits on the dependency chain.
+constexpr int MIN_TILE_THREADS = 128;
 constexpr int MAXN3 = 1024;      // largest n of the pipelined kernel (rank / activation tables in shared memory)
 constexpr int CU_COLS = 32;       // columns per catch-up chunk (one per lane)
 constexpr int CU_PITCH = 36;      // pitch of the staged catch-up vectors (conflict-free B fragments)
-constexpr int NRED = 4;          // reducer CTAs (each sums a quarter of the entries)
-constexpr int AUX_CTA = NRED + 1;
-constexpr int FIRST_WORKER = NRED + 2;
+// Reducer CTAs (Params::nred): 4 on one rank, 8 when sharded.  A reducer thread polls its share of an entry's column of 142
+// partials eight at a time; with 4 CTAs that is three dependent round trips through L2 after the last partial arrived, with 8
+// CTAs (16 sub-sums per entry) two -- on the dependency chain of the sharded runs, where four fewer worker CTAs cost nothing.
+constexpr int NRED_MAX = 8;
 
 struct Params {
     double *S, *gamma, *U, *W;
@@ -110,7 +109,9 @@ struct Params {
     const int32_t *dtab;        // [P][DT_STRIDE] per-pair table (see build_dtab_kernel)
     int nworkers;               // workers that own at least one column
     int granule;                // doubles per ownership quantum (4, 2 or 1)
-    int flat_unr;               // butterflies in flight per thread in the flat phase (3 or 4)
+    int flat_unr;               // butterflies in flight per thread in the flat phase (3, 4 or 5)
+    int tile_threads;           // working threads 0 .. tile_threads-1 do the tile phase, the others the flat phase
+    int nred;                   // CTAs 1 .. nred reduce, CTA nred + 1 keeps gamma / U / W, workers from CTA nred + 2
     int wc_cols;                // row pitch of a worker's private W columns
     double *wg;                 // [nworkers][n][wc_cols] every worker's own columns of W (global, L2-resident, private)
     double *rg;                 // [nworkers][n][n] every worker's copy of the rotation accumulated in this launch, in
@@ -181,6 +182,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int ID, int COUNT>
 __device__ __forceinline__ void named_sync() {
     asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
+__device__ __forceinline__ void named_sync_rt(int id, int count) {       // count: a multiple of 32, same in all participants
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 template <int COUNT>
 __device__ __forceinline__ void named_sync_id(int id) {
@@ -480,7 +484,7 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
                                             int widx, int buf) {
     using VT = typename std::conditional<V == 2, double2, double>::type;
     const int tid = threadIdx.x;
-    const int n = p.n;
+    const int n = p.n, TG = p.tile_threads;
     const long long n1 = n, n2 = n1 * n1;
     const WorkerStep &st = sm.st[buf];
     const bool rot = st.rotated != 0;
@@ -509,16 +513,16 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
         if (widx == 0 && tid == 0) sm.t_d[2] += gtimer() - tc0;
     }
     // ---- flat group: every other row pair of rotation (i, j) inside the owned columns, while the tile group works ------
-    if (tid >= TILE_THREADS) {
-        const bool tmf = (widx == 0 && tid == TILE_THREADS);
+    if (tid >= TG) {
+        const bool tmf = (widx == 0 && tid == TG);
         // (letting the tile group issue its loads first -- a named barrier here, released after its cp.async loop -- was tried:
         // 41.1 -> 44.0 ms per n = 100 cycle, the flat group is the longer of the two on one GPU)
         const unsigned long long tf0 = tmf ? gtimer() : 0;
         if (rot) {
-            const int ft = tid - TILE_THREADS;
-            if (p.flat_unr == 4) flat_update<V, 4>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, FLAT_THREADS);
-            else if (p.flat_unr == 5) flat_update<V, 5>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, FLAT_THREADS);
-            else flat_update<V, 3>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, FLAT_THREADS);
+            const int ft = tid - TG;
+            if (p.flat_unr == 4) flat_update<V, 4>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, (WORK_THREADS - TG));
+            else if (p.flat_unr == 5) flat_update<V, 5>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, (WORK_THREADS - TG));
+            else flat_update<V, 3>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, (WORK_THREADS - TG));
         }
         if (tmf) sm.t_flat += gtimer() - tf0;
         return;
@@ -545,7 +549,7 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
     }
 #pragma unroll
     for (int k = 0; k < WPRE; ++k) {
-        const int idx = tid + k * TILE_THREADS;
+        const int idx = tid + k * TG;
         wv[k] = 0.0;
         if (idx < nother) {
             const int t = f0 + idx / sm.ncols, col = idx - (t - f0) * sm.ncols;
@@ -565,24 +569,24 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
             Rg[(size_t)rj * n + tid] = c * ry - s * rx;
         }
         if (rot)
-            for (int col = tid + TILE_THREADS; col < nact; col += TILE_THREADS) {
+            for (int col = tid + TG; col < nact; col += TG) {
                 const double x = __ldcg(Rg + (size_t)ri * n + col), y = __ldcg(Rg + (size_t)rj * n + col);
                 Rg[(size_t)ri * n + col] = c * x + s * y;
                 Rg[(size_t)rj * n + col] = c * y - s * x;
             }
         if (wrot) rot_col(tid, wx, wy);
         if (rot)
-            for (int col = tid + TILE_THREADS; col < sm.ncols; col += TILE_THREADS)
+            for (int col = tid + TG; col < sm.ncols; col += TG)
                 rot_col(col, __ldcg(Wg + (size_t)i * pitch + col), __ldcg(Wg + (size_t)j * pitch + col));
 #pragma unroll
         for (int k = 0; k < WPRE; ++k) {
-            const int idx = tid + k * TILE_THREADS;
+            const int idx = tid + k * TG;
             if (idx < nother) {
                 const int t = f0 + idx / sm.ncols, col = idx - (t - f0) * sm.ncols;
                 Wr[(size_t)t * pitch + col] = wv[k];
             }
         }
-        for (int idx = tid + WPRE * TILE_THREADS; idx < nother; idx += TILE_THREADS) {
+        for (int idx = tid + WPRE * TG; idx < nother; idx += TG) {
             const int t = f0 + idx / sm.ncols, col = idx - (t - f0) * sm.ncols;
             Wr[(size_t)t * pitch + col] = __ldcg(Wg + (size_t)st.E[t] * pitch + col);
         }
@@ -598,7 +602,7 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
     // orbits {i, j} x f and f x {i, j} (two rows each), same operation order as ever -- and written back.
     auto tile_pass = [&](int t0, int tl) {
         const int tv = tl / V;
-        for (int item = tid; item < e * e * tv; item += TILE_THREADS) {
+        for (int item = tid; item < e * e * tv; item += TG) {
             const int rowidx = item / tv, v = item - rowidx * tv, ea = rowidx / e, eb = rowidx - ea * e;
             const int cc = t0 + v * V;
             const double *g = p.S + sm.piece[piece_of(sm, cc)].base + cc + st.E[ea] * n2 + st.E[eb] * n1;
@@ -606,10 +610,10 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
             if constexpr (V == 2) cp_async_16(dst, g); else cp_async_8(dst, g);
         }
         cp_async_wait_all();
-        named_sync<3, TILE_THREADS>();
+        named_sync_rt(3, TG);
         if (!rot) return;
         const int norb = 1 + 2 * (e - 2);
-        for (int item = tid; item < norb * tv; item += TILE_THREADS) {
+        for (int item = tid; item < norb * tv; item += TG) {
             const int orb = item / tv, v = item - orb * tv;
             const int cc = t0 + v * V;
             double *gbase = p.S + sm.piece[piece_of(sm, cc)].base + cc;
@@ -637,7 +641,7 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
                 *G(f, 0) = q0; *G(f, 1) = q1;
             }
         }
-        named_sync<3, TILE_THREADS>();
+        named_sync_rt(3, TG);
     };
     // dot (piece, q, r, s) over the columns [t0, t0 + tl) of the tile; s varies fastest over the lanes (same tile element:
     // broadcast), the rows a warp reads sit on different banks (TILE_PITCH)
@@ -670,7 +674,7 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
     if (single) {
         tile_pass(0, sm.ncd);
         w_consume();
-        named_sync<3, TILE_THREADS>();
+        named_sync_rt(3, TG);
         if (tm2) {
             const unsigned long long t = gtimer();
             sm.t_pass += t - t_b2;
@@ -683,7 +687,7 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
                 const bool tmd = (widx == 0 && tid == 0);
                 unsigned long long td = tmd ? gtimer() : 0;
                 if (tmd) sm.t_d[0] += td - t_begin;
-                for (int base = 0; base < ndot * 4; base += TILE_THREADS) {
+                for (int base = 0; base < ndot * 4; base += TG) {
                     const int idx4 = base + tid, idx = idx4 >> 2, part = idx4 & 3;
                     double acc = 0.0;
                     if (idx < ndot) {
@@ -705,9 +709,9 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
                     if (part == 0 && idx < ndot) sm.dots[idx] = acc;
                 }
                 if (tmd) { const unsigned long long t = gtimer(); sm.t_d[1] += t - td; td = t; }
-                named_sync<3, TILE_THREADS>();
+                named_sync_rt(3, TG);
                 if (tmd) td = gtimer();
-                for (int en = tid; en < M * M3; en += TILE_THREADS) {
+                for (int en = tid; en < M * M3; en += TG) {
                     const int pp = en / M3, qrs = en - pp * M3;
                     const double *wrow = Wr + (size_t)st.tpos[pp] * pitch;
                     double acc = 0.0;
@@ -725,8 +729,8 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
             }
         }
     } else {
-        constexpr int DACC = (MAX_PIECES * MAXM * MAXM * MAXM + TILE_THREADS - 1) / TILE_THREADS;
-        double dacc[DACC];                           // thread <-> dots (piece, q, r, s) = tid, tid + TILE_THREADS, ...
+        constexpr int DACC = (MAX_PIECES * MAXM * MAXM * MAXM + MIN_TILE_THREADS - 1) / MIN_TILE_THREADS;
+        double dacc[DACC];                           // thread <-> dots (piece, q, r, s) = tid, tid + TG, ...
 #pragma unroll
         for (int h = 0; h < DACC; ++h) dacc[h] = 0.0;
         for (int t0 = 0; t0 < sm.ncd; t0 += TILE_LEN) {
@@ -734,19 +738,19 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
             tile_pass(t0, tl);
             if (t0 == 0) w_consume();
             if (m > 0) {
-                named_sync<3, TILE_THREADS>();
+                named_sync_rt(3, TG);
 #pragma unroll
                 for (int h = 0; h < DACC; ++h)
-                    if (tid + h * TILE_THREADS < ndot) dacc[h] += tile_dot(tid + h * TILE_THREADS, t0, tl);
-                named_sync<3, TILE_THREADS>();        // the tile is overwritten by the next chunk
+                    if (tid + h * TG < ndot) dacc[h] += tile_dot(tid + h * TG, t0, tl);
+                named_sync_rt(3, TG);        // the tile is overwritten by the next chunk
             }
         }
         if (m > 0) {
 #pragma unroll
             for (int h = 0; h < DACC; ++h)
-                if (tid + h * TILE_THREADS < ndot) sm.dots[tid + h * TILE_THREADS] = dacc[h];
-            named_sync<3, TILE_THREADS>();
-            for (int en = tid; en < m * m3; en += TILE_THREADS) post_entry(en);
+                if (tid + h * TG < ndot) sm.dots[tid + h * TG] = dacc[h];
+            named_sync_rt(3, TG);
+            for (int en = tid; en < m * m3; en += TG) post_entry(en);
         }
     }
     if (widx == 0 && tid == 0) {
@@ -846,7 +850,7 @@ __device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm
             const unsigned long long tw0 = gtimer();
             alive = read_record(p, w, acc, c, s) ? 1 : 0;
             sm.t_wait += gtimer() - tw0;
-            if (blockIdx.x == FIRST_WORKER) trace_event(p, w, TR_W_ANGLE);
+            if ((int)blockIdx.x == p.nred + 2) trace_event(p, w, TR_W_ANGLE);
         }
         alive = __shfl_sync(0xffffffffu, alive, 0);
         acc = __shfl_sync(0xffffffffu, acc, 0);
@@ -967,15 +971,15 @@ __device__ __forceinline__ void worker_main(const Params &p, WorkerSmem &sm, dou
 }
 
 // =====================================================================================================================
-// CTAs 1..NRED: reduction of the partial super blocks (fixed order), publication of the total.  Reducer r owns the
-// entries [ne r / NRED, ne (r + 1) / NRED).
+// CTAs 1..nred: reduction of the partial super blocks (fixed order), publication of the total.  Reducer r owns the
+// entries [ne r / nred, ne (r + 1) / nred).
 // =====================================================================================================================
 #ifdef S3_ROLE_NOINLINE
 #define S3_ROLE static __device__ __noinline__
 #else
 #define S3_ROLE __device__ __forceinline__
 #endif
-S3_ROLE void reducer_main(const Params &p, double *scratch /* [8][SB_MAX] smem */, int *flag_sm, int ridx) {
+S3_ROLE void reducer_main(const Params &p, double *scratch /* [THREADS] smem: sub-sums [sub][nl] */, int *flag_sm, int ridx) {
     const int tid = threadIdx.x;
     unsigned long long t_wait = 0, t_red = 0, tq = gtimer();
     if (tid == 0) flag_sm[0] = 0;
@@ -983,7 +987,7 @@ S3_ROLE void reducer_main(const Params &p, double *scratch /* [8][SB_MAX] smem *
     for (int k = 0; k < p.P; ++k) {
         const int slot = k & (SLOTS - 1);
         const int m = p.dtab[(size_t)k * DT_STRIDE];
-        const int ne = m * m * m * m, e_lo = ne * ridx / NRED, e_hi = ne * (ridx + 1) / NRED, nl = e_hi - e_lo;
+        const int ne = m * m * m * m, e_lo = ne * ridx / p.nred, e_hi = ne * (ridx + 1) / p.nred, nl = e_hi - e_lo;
         // `ns` sub-sums per entry over interleaved subsets of the workers: every thread has RLD tagged loads in flight and
         // re-polls a batch until all its tags are those of super block k (with 142 workers and ns = 8 the whole column of an
         // entry is two round trips through L2)
@@ -993,7 +997,7 @@ S3_ROLE void reducer_main(const Params &p, double *scratch /* [8][SB_MAX] smem *
 #define S3_RLD 8
 #endif
         constexpr int RLD = S3_RLD;
-        const int ns = nl > 0 ? max(1, min(8, THREADS / nl)) : 1;
+        const int ns = nl > 0 ? max(1, min(16, THREADS / nl)) : 1;
         const unsigned want = (unsigned)(k + 1);
         const unsigned long long *pb = p.pbuf + (size_t)slot * p.nworkers * SB_MAX * 2;
         bool ok = true;
@@ -1024,13 +1028,13 @@ S3_ROLE void reducer_main(const Params &p, double *scratch /* [8][SB_MAX] smem *
                 for (int u = 0; u < 6; ++u) a8[u] += a8[u + 6];
 #pragma unroll
                 for (int u = 0; u < 3; ++u) a8[u] += a8[u + 3];
-                scratch[sub * SB_MAX + el] = (a8[0] + a8[1]) + a8[2];
+                scratch[sub * nl + el] = (a8[0] + a8[1]) + a8[2];
             } else {
 #pragma unroll
                 for (int w = 4; w > 0; w >>= 1)
 #pragma unroll
                     for (int u = 0; u < w; ++u) a8[u] += a8[u + w];
-                scratch[sub * SB_MAX + el] = a8[0];
+                scratch[sub * nl + el] = a8[0];
             }
         }
         if (!ok) flag_sm[0] = -1;
@@ -1044,7 +1048,7 @@ S3_ROLE void reducer_main(const Params &p, double *scratch /* [8][SB_MAX] smem *
         if (flag_sm[0] < 0) return;
         for (int el = tid; el < nl; el += THREADS) {
             double total = scratch[el];
-            for (int sub = 1; sub < ns; ++sub) total += scratch[sub * SB_MAX + el];
+            for (int sub = 1; sub < ns; ++sub) total += scratch[sub * nl + el];
             const int e = e_lo + el;
             const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
             if (p.nranks > 1) {
@@ -1508,16 +1512,16 @@ __global__ void __launch_bounds__(THREADS, 1) sweep3_kernel(Params p) {
         __syncthreads();
         if (threadIdx.x < SEARCH_THREADS) search_main(p, sm);
         else fetch_main(p, sm);
-    } else if (cta <= NRED) {
+    } else if (cta <= p.nred) {
         double *scratch = reinterpret_cast<double *>(dyn);
-        int *flags = reinterpret_cast<int *>(scratch + 8 * SB_MAX);
+        int *flags = reinterpret_cast<int *>(scratch + THREADS);
         reducer_main(p, scratch, flags, cta - 1);
-    } else if (cta == AUX_CTA) {
+    } else if (cta == p.nred + 1) {
         int *flags = reinterpret_cast<int *>(dyn);
         double *cs = reinterpret_cast<double *>(dyn + 64);
         aux_main(p, flags, cs);
     } else {
-        const int widx = cta - FIRST_WORKER;
+        const int widx = cta - (p.nred + 2);
         if (widx >= p.nworkers) return;
         WorkerSmem &sm = *reinterpret_cast<WorkerSmem *>(dyn);
         double *Wr = reinterpret_cast<double *>(dyn + ((sizeof(WorkerSmem) + 15) / 16) * 16);
@@ -1555,15 +1559,16 @@ size_t sweep3_mailbox_bytes(int nranks) {
 #endif
 
 // Shared memory of a worker for this problem, or 0 if the pipelined kernel cannot take it.
-static size_t worker_smem_bytes(int n, int na, int grid, int &nworkers, int &granule, int &wc_cols) {
+static size_t worker_smem_bytes(int n, int na, int grid, int nred, int &nworkers, int &granule, int &wc_cols) {
     using namespace S3_NS;
-    if (grid < FIRST_WORKER + 1 || n > MAXN3 || na < 1) return 0;
+    const int first_worker = nred + 2;
+    if (grid < first_worker + 1 || n > MAXN3 || na < 1) return 0;
 #ifndef S3_GRANULE_MAX
 #define S3_GRANULE_MAX 4
 #endif
     granule = (n % 4 == 0 && S3_GRANULE_MAX >= 4) ? 4 : ((n % 2 == 0) ? 2 : 1);
     const long long qrow = n / granule, Q = (long long)na * qrow;
-    nworkers = (int)std::min<long long>(grid - FIRST_WORKER, Q);
+    nworkers = (int)std::min<long long>(grid - first_worker, Q);
     // the longest owned range, and the most pieces it can break into
     const long long per = (Q + nworkers - 1) / nworkers;
     const long long pieces = (per + qrow - 1) / qrow + 1;
@@ -1576,7 +1581,8 @@ static size_t worker_smem_bytes(int n, int na, int grid, int &nworkers, int &gra
 #ifndef QIO_S3_TIMED
 bool sweep3_supported(int n, int na) {
     int nw, g, cols;
-    const size_t b = worker_smem_bytes(n, na, sm_count(), nw, g, cols);
+    // with the larger reducer count (fewer workers): what fits then fits with four reducers as well
+    const size_t b = worker_smem_bytes(n, na, sm_count(), S3_NS::NRED_MAX, nw, g, cols);
     return b > 0 && b <= 200 * 1024;
 }
 
@@ -1589,7 +1595,8 @@ int S3_LAUNCH(double *gamma, double *S, double *U, double *W, int n, int a0, int
     using namespace S3_NS;
     const int grid = sm_count();
     Params p;
-    const size_t wsm = worker_smem_bytes(n, na, grid, p.nworkers, p.granule, p.wc_cols);
+    p.nred = (h_peers && h_peers->nranks > 1) ? NRED_MAX : 4;
+    const size_t wsm = worker_smem_bytes(n, na, grid, p.nred, p.nworkers, p.granule, p.wc_cols);
     if (!(wsm > 0 && wsm <= 200 * 1024)) {
         set_error("sweep_cycle: problem does not fit the pipelined kernel");
         return QIO_B200_ERR_UNSUPPORTED;
@@ -1625,6 +1632,11 @@ int S3_LAUNCH(double *gamma, double *S, double *U, double *W, int n, int a0, int
 #define S3_FLAT_UNR 5
 #endif
     p.flat_unr = S3_FLAT_UNR;      // butterflies in flight per thread of the flat group (3, 4 or 5)
+#ifndef S3_TILE_THREADS_SMALL
+#define S3_TILE_THREADS_SMALL 256
+#endif
+    // bytes one rotation reads on this rank: a large share -> the flat phase is the longer one -> more flat threads
+    p.tile_threads = (32.0 * (double)n * n * na < 20e6) ? S3_TILE_THREADS_SMALL : MIN_TILE_THREADS;
     p.blocks_out = opts.blocks_out;
     p.trace = opts.trace_out;
     p.trace_k0 = opts.trace_first_pair;
@@ -1639,7 +1651,7 @@ int S3_LAUNCH(double *gamma, double *S, double *U, double *W, int n, int a0, int
     QIO_REQUIRE(p.nranks == 1 || (p.epoch >= 1 && p.epoch < (1u << (32 - LL_STEP_BITS))), "sweep_cycle: mailbox epoch must be in 1..4095");
     p.mailboxes = p.nranks > 1 ? reinterpret_cast<double *const *>(h_peers->mailboxes) : nullptr;
     size_t dyn = std::max(wsm, sizeof(SearchSmem));
-    dyn = std::max(dyn, sizeof(double) * 8 * SB_MAX + 256);
+    dyn = std::max(dyn, sizeof(double) * THREADS + 256);
     QIO_CUDA(cudaFuncSetAttribute(sweep3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int blocks_per_sm = 0;
     QIO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sweep3_kernel, THREADS, dyn));
