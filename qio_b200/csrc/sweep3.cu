@@ -69,14 +69,16 @@ constexpr int TILE_PITCH = 98;   // row pitch of the tile: 196 words = 4 mod 32,
 constexpr int DT_STRIDE = 16;     // ints per entry of the per-pair table
 constexpr int WORK_THREADS = THREADS - 32;   // a worker's warps 0..14 compute, warp 15 plans the next step (polls the angle)
 // The two phases of a worker step touch disjoint rows (the flat phase leaves the rows of the tile alone), so they run
-// CONCURRENTLY on two groups of warps: warps 0..3 the latency-bound tile phase (rows of the next super block: load, rotate,
-// dot products, post), the other working warps the bandwidth-bound flat phase (everything else of the rotation).  A step then lasts
-// max(tile, flat) instead of tile + flat.  (Round 1 tried this split and dropped it: with a fixed four butterflies in flight per
-// thread the smaller flat group could not keep enough loads in flight; the flat group now runs five, and the tile group's
-// loads are cp.async, one round trip whatever its size.)
-// The split is chosen per launch (Params::tile_threads): 128 tile threads where the flat phase is the longer one (one GPU, n = 100:
-// 96 / 128 / 160 / 192 -> 46.3 / 41.3 / 41.6 / 41.6 ms per cycle), more where a rank's share of the rotation is small and the
-// tile phase sits on the dependency chain.
+// CONCURRENTLY on two groups of warps: the first Params::tile_threads working threads the latency-bound tile phase (rows of the
+// next super block: load, rotate, dot products, post), the others the bandwidth-bound flat phase (everything else of the
+// rotation).  A step then lasts max(tile, flat) instead of tile + flat.  Both groups load asynchronously: the tile group with
+// cp.async into the tile (one round trip whatever its size), the flat group with cp.async into private staging slots, two
+// batches of four butterflies in flight per thread (flat_update_staged).  The requests of the two groups share the SM's memory
+// pipeline, and the tile loads -- on the dependency chain -- queue behind the flat ones: deeper flat batches are SLOWER
+// (n = 100, one GPU, 128 tile threads: registers-only 41.4 ms per cycle, staged 3 / 4 / 6 per batch 42.3 / 42.7 / 43.6), what
+// pays is the larger tile group the cheaper flat phase affords (staged 4: 128 / 160 / 192 / 224 / 256 / 288 / 320 tile threads
+// -> 42.7 / 41.7 / 39.8 / 39.0 / 39.1 / 40.4 / 42.8 ms; n = 200: 1133 registers-only -> 1109 ms at 224).
+// The split is chosen per launch: 224 tile threads, 256 where a rank's share of the rotation is small (sharded runs).
 constexpr int MIN_TILE_THREADS = 128;
 constexpr int MAXN3 = 1024;      // largest n of the pipelined kernel (rank / activation tables in shared memory)
 constexpr int CU_COLS = 32;       // columns per catch-up chunk (one per lane)
@@ -109,7 +111,8 @@ struct Params {
     const int32_t *dtab;        // [P][DT_STRIDE] per-pair table (see build_dtab_kernel)
     int nworkers;               // workers that own at least one column
     int granule;                // doubles per ownership quantum (4, 2 or 1)
-    int flat_unr;               // butterflies in flight per thread in the flat phase (3, 4 or 5)
+    int flat_unr;               // butterflies in flight per thread in the flat phase (3, 4 or 5), register version
+    int flat_batch;             // staged flat phase: butterflies per cp.async batch (2, 3 or 4; two batches in flight), 0: register version
     int tile_threads;           // working threads 0 .. tile_threads-1 do the tile phase, the others the flat phase
     int nred;                   // CTAs 1 .. nred reduce, CTA nred + 1 keeps gamma / U / W, workers from CTA nred + 2
     int wc_cols;                // row pitch of a worker's private W columns
@@ -178,6 +181,11 @@ __device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 template <int ID, int COUNT>
 __device__ __forceinline__ void named_sync() {
@@ -396,6 +404,100 @@ static __device__ __noinline__ void flat_update(double *__restrict__ S, const Wo
     }
 }
 
+// The same phase with the loads staged through shared memory: every thread owns 2 x B private 2-row slots and keeps two
+// cp.async batches of B butterflies in flight -- batch b + 1 is issued before batch b is waited for, so between B and 2 B
+// butterflies per thread are outstanding at any time (the register version drains to zero at every round trip), and the
+// data in flight costs no registers, only the element offsets for the write-back.  No barrier: a slot is written (by the
+// copy engine) and read by its own thread only.  Item order, arithmetic and stores are those of flat_update.
+template <int V, int B>
+static __device__ __noinline__ void flat_update_staged(double *__restrict__ S, const WorkerSmem *smp, const short *flatlist, int nflat,
+                                                       int n, int i, int j, double c, double s, int t, int nt, void *stage_raw) {
+    using VT = typename std::conditional<V == 2, double2, double>::type;
+    const WorkerSmem &sm = *smp;
+    VT *stage = reinterpret_cast<VT *>(stage_raw) + t;      // slot (batch buffer h, u, row r) at stage[((h B + u) 2 + r) nt]
+    const long long n1 = n, n2 = n1 * n1;
+    const int lv = sm.ncd / V;
+    const long long b0 = sm.piece[0].base, b1 = sm.piece[1].base, b2 = sm.piece[2].base, b3 = sm.piece[3].base;
+    const int c1 = sm.npieces > 1 ? sm.piece[1].col0 : 0x7fffffff, c2 = sm.npieces > 2 ? sm.piece[2].col0 : 0x7fffffff,
+              c3 = sm.npieces > 3 ? sm.piece[3].col0 : 0x7fffffff;
+    const int dq = nt / lv, dr = nt - dq * lv;
+    const long long last = 2LL * nflat * lv;
+    long long item = t;
+    int rho2 = (int)(item / lv), v = (int)(item - (long long)rho2 * lv);
+    long long off[2][B];            // element offset of the butterfly's row-pair origin, bit 62 = axis, negative = no item
+    auto rows = [&](long long o, long long &si, long long &sj) -> long long {
+        const bool ax = (o >> 62) & 1;
+        si = ax ? (long long)i * n1 : (long long)i * n2;
+        sj = ax ? (long long)j * n1 : (long long)j * n2;
+        return o & ~(1LL << 62);
+    };
+    auto issue = [&](auto hc) -> bool {
+        constexpr int h = decltype(hc)::value;
+        const bool any = item < last;
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            long long o = -1;
+            if (item < last) {
+                const int axis = rho2 >= nflat ? 1 : 0, xx = flatlist[rho2 - axis * nflat];
+                const int cc = v * V;
+                const long long pb = cc >= c3 ? b3 : (cc >= c2 ? b2 : (cc >= c1 ? b1 : b0));
+                o = (pb + cc + (axis ? xx * n2 : xx * n1)) | ((long long)axis << 62);
+                long long si, sj;
+                const long long oo = rows(o, si, sj);
+                VT *slot = stage + (size_t)((h * B + u) * 2) * nt;
+                if constexpr (V == 2) {
+                    cp_async_16(slot, S + oo + si);
+                    cp_async_16(slot + nt, S + oo + sj);
+                } else {
+                    cp_async_8(slot, S + oo + si);
+                    cp_async_8(slot + nt, S + oo + sj);
+                }
+            }
+            off[h][u] = o;
+            item += nt;
+            v += dr;
+            rho2 += dq;
+            if (v >= lv) {
+                v -= lv;
+                ++rho2;
+            }
+        }
+        cp_async_commit();
+        return any;
+    };
+    auto process = [&](auto hc) {
+        constexpr int h = decltype(hc)::value;
+#pragma unroll
+        for (int u = 0; u < B; ++u)
+            if (off[h][u] >= 0) {
+                long long si, sj;
+                const long long o = rows(off[h][u], si, sj);
+                const VT *slot = stage + (size_t)((h * B + u) * 2) * nt;
+                const VT x = slot[0], y = slot[nt];
+                if constexpr (V == 2) {
+                    *reinterpret_cast<VT *>(S + o + si) = make_double2(c * x.x + s * y.x, c * x.y + s * y.y);
+                    *reinterpret_cast<VT *>(S + o + sj) = make_double2(c * y.x - s * x.x, c * y.y - s * x.y);
+                } else {
+                    *reinterpret_cast<VT *>(S + o + si) = c * x + s * y;
+                    *reinterpret_cast<VT *>(S + o + sj) = c * y - s * x;
+                }
+            }
+    };
+    using H0 = std::integral_constant<int, 0>;
+    using H1 = std::integral_constant<int, 1>;
+    bool more = issue(H0{});
+    while (more) {
+        const bool more1 = issue(H1{});
+        cp_async_wait_group<1>();
+        process(H0{});
+        if (!more1) break;
+        more = issue(H0{});
+        cp_async_wait_group<1>();
+        process(H1{});
+    }
+    cp_async_wait_group<0>();
+}
+
 // Dormant orbitals.  An orbital x that has not yet appeared in any super block of this launch cannot take part in a
 // rotation, so the flat phase skips every row pair whose free index is x: rows (i|j, x) of axis-1 rotations and rows
 // (x, i|j) of axis-2 rotations -- on average a third of the update traffic of a cycle.  What those rows missed is the
@@ -520,7 +622,10 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
         const unsigned long long tf0 = tmf ? gtimer() : 0;
         if (rot) {
             const int ft = tid - TG;
-            if (p.flat_unr == 4) flat_update<V, 4>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, (WORK_THREADS - TG));
+            if (p.flat_batch == 4) flat_update_staged<V, 4>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, (WORK_THREADS - TG), cu_in);
+            else if (p.flat_batch == 3) flat_update_staged<V, 3>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, (WORK_THREADS - TG), cu_in);
+            else if (p.flat_batch == 2) flat_update_staged<V, 2>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, (WORK_THREADS - TG), cu_in);
+            else if (p.flat_unr == 4) flat_update<V, 4>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, (WORK_THREADS - TG));
             else if (p.flat_unr == 5) flat_update<V, 5>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, (WORK_THREADS - TG));
             else flat_update<V, 3>(p.S, &sm, sm.flatlist[buf], sm.nflat[buf], n, i, j, c, s, ft, (WORK_THREADS - TG));
         }
@@ -832,6 +937,9 @@ __device__ __forceinline__ void plan_worker_step(const Params &p, WorkerSmem &sm
     } else if (lane == 0) {
         sm.nflat[buf] = 0;
     }
+    // (an L2 prefetch of the tile rows one, two or four steps ahead from here -- cp.async.bulk.prefetch.L2 per row segment --
+    // changed nothing: 39.0 -> 39.1 / 39.1 / 40.0 ms per n = 100 cycle; the tile loads do not wait for DRAM but behind the flat
+    // group's requests of the same SM)
     if (has) st.D[lane] = Dq;
     if (lane == 0) {
         st.i = i;
@@ -1636,7 +1744,30 @@ int S3_LAUNCH(double *gamma, double *S, double *U, double *W, int n, int a0, int
 #define S3_TILE_THREADS_SMALL 256
 #endif
     // bytes one rotation reads on this rank: a large share -> the flat phase is the longer one -> more flat threads
-    p.tile_threads = (32.0 * (double)n * n * na < 20e6) ? S3_TILE_THREADS_SMALL : MIN_TILE_THREADS;
+#ifndef S3_TILE_THREADS_LARGE
+#define S3_TILE_THREADS_LARGE 224
+#endif
+    p.tile_threads = (32.0 * (double)n * n * na < 20e6) ? S3_TILE_THREADS_SMALL : S3_TILE_THREADS_LARGE;
+    // staged flat phase: 2 batches x B butterflies x 2 rows x 16 bytes (8 for odd n) per flat thread, on top of the catch-up
+    // staging area (never live at the same time); the largest batch that fits into the 227 KB of an SM
+#ifndef S3_FLAT_BATCH_MAX
+#define S3_FLAT_BATCH_MAX 4
+#endif
+    size_t wsm_staged = wsm;
+    p.flat_batch = 0;
+    {
+        const size_t cu_bytes = sizeof(double) * (size_t)n * CU_PITCH, slot = (n & 1) ? 8 : 16;
+        const int batches[3] = {4, 3, 2};
+        for (int b : batches) {
+            const size_t stage = 2 * (size_t)b * 2 * (size_t)(WORK_THREADS - p.tile_threads) * slot;
+            const size_t total = wsm - cu_bytes + std::max(cu_bytes, stage);
+            if (b <= S3_FLAT_BATCH_MAX && total <= 227 * 1024) {
+                p.flat_batch = b;
+                wsm_staged = total;
+                break;
+            }
+        }
+    }
     p.blocks_out = opts.blocks_out;
     p.trace = opts.trace_out;
     p.trace_k0 = opts.trace_first_pair;
@@ -1650,7 +1781,7 @@ int S3_LAUNCH(double *gamma, double *S, double *U, double *W, int n, int a0, int
     p.epoch = h_peers ? h_peers->epoch : 0u;
     QIO_REQUIRE(p.nranks == 1 || (p.epoch >= 1 && p.epoch < (1u << (32 - LL_STEP_BITS))), "sweep_cycle: mailbox epoch must be in 1..4095");
     p.mailboxes = p.nranks > 1 ? reinterpret_cast<double *const *>(h_peers->mailboxes) : nullptr;
-    size_t dyn = std::max(wsm, sizeof(SearchSmem));
+    size_t dyn = std::max(wsm_staged, sizeof(SearchSmem));
     dyn = std::max(dyn, sizeof(double) * THREADS + 256);
     QIO_CUDA(cudaFuncSetAttribute(sweep3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int blocks_per_sm = 0;
