@@ -17,11 +17,17 @@
 //   * B (the rotation matrix, <= 104 columns per CTA) is resident in shared memory for the whole kernel, k-major with a
 //     pitch = 2 mod 16 doubles (conflict-free for the same k-groups);
 //   * the N tiles are split 7 + 6 between the two warp columns (warps w and w + 4 share a scheduler), so that n = 100 is
-//     padded to 104 columns instead of 112 (skipping the empty half of the last K slab when K = 4 mod 8 was tried and
-//     dropped: the run-time test in the unrolled k-group loop cost 4-7 %, more than the 4 % of the tensor work it saved);
+//     padded to 104 columns instead of 112; when the upper half of the last K slab is padding (K = 1..4 mod 8) that slab runs
+//     one k-group instead of two, as a second fully unrolled copy of the slab body (a run-time bound on the k-group loop
+//     cost 4-7 %, more than it saved);
+//   * no division on the hot path: the ring position / phase and the (batch, M tile) decomposition are running counters (a
+//     64-bit q % stages per slab was 10 % of the stall samples, the B prologue another 5 %: the producer now starts
+//     streaming while the consumers load B eight elements in flight per thread);
 //   * batched: `batch` independent problems of the same shape (the slabs of a leading-index shard, qio_b200_rotate_axis_batched)
 //     are one launch -- the tensor map has the batch as its fourth dimension and the persistent tile loop runs over
 //     (batch, M tile).
+#include <type_traits>
+
 #include "tma.cuh"
 
 namespace qio {
@@ -70,28 +76,49 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
         }
         mbar_fence_init();
     }
-    // B: sB[k][c] = U[n0 + c][k], zero beyond (kdim, ncols)
-    for (int e = tid; e < kpad * np; e += RT_THREADS) {
-        const int c = e / kpad, k = e - c * kpad;       // k fastest: coalesced reads of a row of U
-        if (c < np) sB[(size_t)k * np + c] = (c < ncols && k < kdim) ? U[(long long)(n0 + c) * ldu + k] : 0.0;
-    }
     __syncthreads();
 
     if (warp == RT_CONSUMERS / 32) {
-        // ---- producer warp: one lane streams the slabs of all tiles of this CTA through the ring -------------------
+        // ---- producer warp: one lane streams the slabs of all tiles of this CTA through the ring (it starts while the
+        // consumers are still loading B).  Stage index and phase are running counters: a 64-bit q % stages per slab in every
+        // warp was 10 % of the kernel's stall samples (profiles/r2_final_summary.md) ---------------------------------------
         if (lane == 0) {
-            long long q = 0;
-            for (long long tile = blockIdx.x; tile < mtiles; tile += gridDim.x)
-                for (int ks = 0; ks < nslabs; ++ks, ++q) {
-                    const int s = (int)(q % stages);
-                    if (q >= stages) mbar_wait(empty + s, (unsigned)(((q / stages) - 1) & 1));
+            int s = 0;
+            unsigned ph = 1;            // parity of the "empty" completion to wait for: none in the first round
+            bool first_round = true;
+            int b = (int)(blockIdx.x / mtiles_b), mt = (int)(blockIdx.x - b * mtiles_b);       // tile = b * mtiles_b + mt
+            for (long long tile = blockIdx.x; tile < mtiles; tile += gridDim.x) {
+                for (int ks = 0; ks < nslabs; ++ks) {
+                    if (!first_round) mbar_wait(empty + s, ph);
                     mbar_expect_tx(full + s, RT_STAGE_DOUBLES * sizeof(double));
-                    const long long b = tile / mtiles_b, mt = tile - b * mtiles_b;
-                    tma_load_4d(sA + (size_t)s * RT_STAGE_DOUBLES, &tmA, 0, ks * RT_KS, (int)(mt * (RT_BM / 16)), (int)b, full + s);
+                    tma_load_4d(sA + (size_t)s * RT_STAGE_DOUBLES, &tmA, 0, ks * RT_KS, mt * (RT_BM / 16), b, full + s);
+                    if (++s == stages) {
+                        s = 0;
+                        ph ^= 1u;
+                        first_round = false;
+                    }
                 }
+                for (mt += (int)gridDim.x; mt >= mtiles_b; mt -= (int)mtiles_b) ++b;
+            }
         }
         return;
     }
+
+    // B: sB[k][c] = U[n0 + c][k], zero beyond (kdim, ncols); eight loads in flight per consumer thread
+    for (int base = 0; base < kpad * np; base += 8 * RT_CONSUMERS) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = base + u * RT_CONSUMERS + tid, c = e / kpad, k = e - c * kpad;       // k fastest: coalesced reads of a row of U
+            v[u] = (e < kpad * np && c < ncols && k < kdim) ? U[(long long)(n0 + c) * ldu + k] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = base + u * RT_CONSUMERS + tid, c = e / kpad, k = e - c * kpad;
+            if (e < kpad * np) sB[(size_t)k * np + c] = v[u];
+        }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(RT_CONSUMERS) : "memory");
 
     // ---- consumers: 8 warps as 4 (M) x 2 (N) -------------------------------------------------------------------
     const int g = lane >> 2, t = lane & 3;
@@ -110,60 +137,93 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
         a_unit[mi] = (mm & 15) >> 1;
         a_low[mi] = mm & 1;
     }
-    long long q = 0;
+    int s = 0;
+    unsigned ph = 0;                    // parity of the "full" completion to wait for
+    // kdim = 1..4 mod 8: rows 4..7 of the last slab are padding (zero-filled by the TMA unit, zero in B)
+    const bool half_last = (kdim % RT_KS) != 0 && (kdim % RT_KS) <= RT_KS / 2;
+    int tb = (int)(blockIdx.x / mtiles_b), tmt = (int)(blockIdx.x - tb * mtiles_b);       // tile = tb * mtiles_b + tmt (no division per tile)
     for (long long tile = blockIdx.x; tile < mtiles; tile += gridDim.x) {
         double acc[4][RT_MAX_NT][2];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
             for (int ni = 0; ni < RT_MAX_NT; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        for (int ks = 0; ks < nslabs; ++ks, ++q) {
-            const int s = (int)(q % stages);
-            mbar_wait(full + s, (unsigned)((q / stages) & 1));
+        // one slab = two k-groups of 4 rows; all fragments of the slab are loaded before its DMMAs (one exposed shared-memory
+        // latency per slab).  When the upper half of the last slab is padding that slab runs one k-group only -- as a second,
+        // fully unrolled copy of the body (a run-time bound on the k-group loop cost more than it saved).
+        auto slab = [&](auto ngrp_c, int ks) {
+            constexpr int NG = decltype(ngrp_c)::value;
+            mbar_wait(full + s, ph);
             const double *a = sA + (size_t)s * RT_STAGE_DOUBLES;
             const double *b = sB + (size_t)(ks * RT_KS) * np + wn + g;
+            double af[NG][4], bf[NG][RT_MAX_NT];
 #pragma unroll
-            for (int grp = 0; grp < 2; ++grp) {
-                const int r = 2 * t + grp;          // k-group: rows {0, 2, 4, 6} (+1) of the slab
-                double af[4], bf[RT_MAX_NT];
+            for (int grp = 0; grp < NG; ++grp) {
+                // k-groups of a full slab: rows {0, 2, 4, 6}, then {1, 3, 5, 7} (conflict-free fragment loads); the single
+                // k-group of a half-empty last slab: rows 0..3 (two-way conflicts, once per tile)
+                const int r = NG == 2 ? 2 * t + grp : t;
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi)
-                    af[mi] = a[(a_line[mi] + r) * 16 + ((a_unit[mi] ^ r) << 1) + a_low[mi]];
+                    af[grp][mi] = a[(a_line[mi] + r) * 16 + ((a_unit[mi] ^ r) << 1) + a_low[mi]];
 #pragma unroll
-                for (int ni = 0; ni < RT_MAX_NT; ++ni) bf[ni] = ni < nt ? b[(size_t)r * np + 8 * ni] : 0.0;
+                for (int ni = 0; ni < RT_MAX_NT; ++ni) bf[grp][ni] = ni < nt ? b[(size_t)r * np + 8 * ni] : 0.0;
+            }
+#pragma unroll
+            for (int grp = 0; grp < NG; ++grp)
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                     for (int ni = 0; ni < RT_MAX_NT; ++ni)
-                        if (ni < nt) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
-            }
+                        if (ni < nt) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[grp][mi], bf[grp][ni]);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + s);
-        }
+            if (++s == stages) {
+                s = 0;
+                ph ^= 1u;
+            }
+        };
+        const int nfull = half_last ? nslabs - 1 : nslabs;
+        // (starting the second warp column a few slabs late, so that the epilogues of the two warps of a scheduler do not
+        // coincide, changed nothing: 0.697 -> 0.700 ms per n = 100 pass)
+        for (int ks = 0; ks < nfull; ++ks) slab(std::integral_constant<int, 2>{}, ks);
+        if (half_last) slab(std::integral_constant<int, 1>{}, nslabs - 1);
         // epilogue: C fragment (row g, cols 2t, 2t+1) of each 8x8 tile
-        const long long bidx = tile / mtiles_b, m0 = (tile - bidx * mtiles_b) * RT_BM;
-        double *outb = out + bidx * bs_out;
+        const long long m0 = (long long)tmt * RT_BM;
+        double *outb = out + (long long)tb * bs_out;
+        const int colw = n0 + wn + 2 * t, cend = n0 + ncols;
+        if (LEAD_KEEP) {
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-            const long long m = m0 + wm + 8 * mi + g;
-            if (m >= rows) continue;
+            for (int mi = 0; mi < 4; ++mi) {
+                const long long m = m0 + wm + 8 * mi + g;
+                if (m >= rows) continue;
+                double *o = outb + (long long)colw * ld_out + m;
 #pragma unroll
-            for (int ni = 0; ni < RT_MAX_NT; ++ni) {
-                if (ni >= nt) continue;
-                const int col = n0 + wn + 8 * ni + 2 * t;
-                if (LEAD_KEEP) {
-                    if (col < n0 + ncols) outb[(long long)col * ld_out + m] = acc[mi][ni][0];
-                    if (col + 1 < n0 + ncols) outb[(long long)(col + 1) * ld_out + m] = acc[mi][ni][1];
-                } else {
-                    double *orow = outb + m * ld_out;
-                    if (col + 1 < n0 + ncols) {
-                        *reinterpret_cast<double2 *>(orow + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-                    } else if (col < n0 + ncols) {
-                        orow[col] = acc[mi][ni][0];
+                for (int ni = 0; ni < RT_MAX_NT; ++ni) {
+                    if (ni >= nt) continue;
+                    const int col = colw + 8 * ni;
+                    if (col < cend) o[(long long)(8 * ni) * ld_out] = acc[mi][ni][0];
+                    if (col + 1 < cend) o[(long long)(8 * ni + 1) * ld_out] = acc[mi][ni][1];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const long long m = m0 + wm + 8 * mi + g;
+                if (m >= rows) continue;
+                double *o = outb + m * ld_out + colw;
+#pragma unroll
+                for (int ni = 0; ni < RT_MAX_NT; ++ni) {
+                    if (ni >= nt) continue;
+                    const int col = colw + 8 * ni;
+                    if (col + 1 < cend) {
+                        *reinterpret_cast<double2 *>(o + 8 * ni) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                    } else if (col < cend) {
+                        o[8 * ni] = acc[mi][ni][0];
                     }
                 }
             }
         }
+        for (tmt += (int)gridDim.x; tmt >= mtiles_b; tmt -= (int)mtiles_b) ++tb;
     }
 }
 

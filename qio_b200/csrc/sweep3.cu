@@ -617,8 +617,8 @@ __device__ __forceinline__ void worker_step(const Params &p, WorkerSmem &sm, dou
     // ---- flat group: every other row pair of rotation (i, j) inside the owned columns, while the tile group works ------
     if (tid >= TG) {
         const bool tmf = (widx == 0 && tid == TG);
-        // (letting the tile group issue its loads first -- a named barrier here, released after its cp.async loop -- was tried:
-        // 41.1 -> 44.0 ms per n = 100 cycle, the flat group is the longer of the two on one GPU)
+        // (letting the tile group issue its loads first -- a named barrier here, released after its cp.async loop -- was tried
+        // twice: 41.1 -> 44.0 ms per n = 100 cycle with the register flat phase, 39.0 -> 41.0 ms with the staged one)
         const unsigned long long tf0 = tmf ? gtimer() : 0;
         if (rot) {
             const int ft = tid - TG;
