@@ -393,6 +393,8 @@ def single_gpu_leg(args, n, steps, warmup, local_rank, detail):
     engine = dev.sweep_engine(n)
     torch.cuda.reset_peak_memory_stats()
 
+    sweep_events = []           # CUDA events around the sweep kernel of every device_step
+
     def device_step():
         """The whole hot path with every input already in HBM."""
         dev.prep_rdm12(dm1_d, dm2_d, n, gamma=gamma, Gamma=Gamma)
@@ -406,7 +408,11 @@ def single_gpu_leg(args, n, steps, warmup, local_rank, detail):
         mi = dev.mutual_information_matrix(s1, s_pair, allpairs_d, n)      # ... and the mutual-information matrix
         Ud = U0_d.clone()
         dev.sweep_reset(W, n)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
         res, summary = dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs, blocks_out=blocks_sweep)
+        ev[1].record()
+        sweep_events.append(ev)
         strict = dev.pair_linesearch(blocks_sweep, pairs_d, mask, tabs, strict_order=True)      # decision audit
         diag = dev.deferred_diagonals(g, Gamma, W, n, inds_d)
         _, _, _, esum = dev.orbital_entropies(diag, want_spec=False)
@@ -455,12 +461,14 @@ def single_gpu_leg(args, n, steps, warmup, local_rank, detail):
     time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    del sweep_events[:]
     e0.record()
     for _ in range(steps):
         device_step()
     e1.record()
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
+    sweep_in_step = [a.elapsed_time(b) for a, b in sweep_events]      # the dominant kernel inside the timed region
     clocks = sampler.stop()
     ms_per_step = ms_total / steps
     value = evals_per_step / (ms_per_step * 1e-3)
@@ -505,8 +513,10 @@ def single_gpu_leg(args, n, steps, warmup, local_rank, detail):
         return g_, U0_d.clone()
 
     g, Ud = fresh_state()
-    sweep_ms = timed(lambda: dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs), 1)
+    phases['jacobi_cycle_kernel_alone_ms'] = timed(lambda: dev.sweep_cycle(g, Gamma, Ud, W, n, pairs_d, mask, tabs), 1)
+    sweep_ms = float(np.mean(sweep_in_step))        # average launch duration over the timed steps (CUDA events, same stream)
     phases['jacobi_cycle_kernel_ms'] = sweep_ms
+    phases['jacobi_cycle_kernel_ms_each'] = sweep_in_step
     phases['sweep_flush_ms'] = timed(lambda: dev.sweep_flush(Gamma, W, n, work), 1)
     if detail:
         g, Ud = fresh_state()
@@ -544,7 +554,7 @@ def single_gpu_leg(args, n, steps, warmup, local_rank, detail):
     roofline = {'kernel': kname,
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'peak_source': peak_src, 'traffic': traffic, 'traffic_source': traffic_src, 'algorithmic_bytes_per_launch': algo_bytes,
-                'avg_launch_ms': sweep_ms, 'launches_timed': 1,
+                'avg_launch_ms': sweep_ms, 'launches_timed': len(sweep_in_step),
                 'moved_bytes_per_launch': moved,
                 'frac_moved': moved / (sweep_ms * 1e-3) / 1e9 / peak,
                 'frac_dram': (traffic / (sweep_ms * 1e-3) / 1e9 / peak) if traffic else None,
@@ -735,6 +745,8 @@ def multi_gpu_leg(args, n, steps, warmup, rank, world, local_rank, peers, detail
     torch.cuda.reset_peak_memory_stats()
     mem_before = torch.cuda.memory_allocated()
 
+    sweep_events = []           # CUDA events around the sweep kernel of every step
+
     def step(dm1_in, dm2_in):
         state.pop('st', None)       # release the previous step's shard buffers before the new ones are allocated
         st = ShardedRDM.from_solver(dm1_in, dm2_in, n, peers=peers)
@@ -744,6 +756,7 @@ def multi_gpu_leg(args, n, steps, warmup, rank, world, local_rank, peers, detail
         Ud = U0_d.clone()
         dev.sweep_reset(W, n)
         rec, n_acc, cost, flags = st.sweep_cycle(Ud, W, pairs_np, mask, inds_d, tabs)      # includes the decision audit
+        sweep_events.append(st.last_sweep_events)
         st.flush(W)
         state.update(rec_all=rec_all, rec=rec, n_acc=n_acc, cost=cost, U=Ud, st=st, mi=mi, audit=st.last_audit)
 
@@ -778,8 +791,13 @@ def multi_gpu_leg(args, n, steps, warmup, rank, world, local_rank, peers, detail
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / k, sampler.stop()
 
+    del sweep_events[:]
     ms_per_step, clocks = timed_steps(dm1_d, dm2_d, steps)
     value = evals_per_step / (ms_per_step * 1e-3)
+    # the dominant kernel inside the timed region: per launch the slowest rank, then the average over the launches
+    sw = torch.tensor([a.elapsed_time(b) for a, b in sweep_events], dtype=torch.float64, device='cuda')
+    dist.all_reduce(sw, op=dist.ReduceOp.MAX)
+    sweep_in_step = [float(x) for x in sw.tolist()]
     e2e = None
     if not args.no_e2e:
         step(dm1_h, dm2_h)
@@ -811,9 +829,12 @@ def multi_gpu_leg(args, n, steps, warmup, rank, world, local_rank, peers, detail
     Ud = U0_d.clone()
     dev.sweep_reset(W, n)
     pairs_d = dev.to_device(pairs_np, dev.I32)
-    sweep_ms, (_, summ) = tmax(lambda: dev.sweep_cycle(st.gamma, st.G, Ud, W, n, pairs_d, mask, tabs, st.a0, st.na, peers))
+    alone_ms, (_, summ) = tmax(lambda: dev.sweep_cycle(st.gamma, st.G, Ud, W, n, pairs_d, mask, tabs, st.a0, st.na, peers))
     n_acc = int(dev.to_host(summ)[0])
+    phases['jacobi_cycle_kernel_alone_ms'] = alone_ms      # one extra launch after a barrier: launch skew of the ranks is inside
+    sweep_ms = float(np.mean(sweep_in_step))               # average launch duration over the timed steps (max over ranks each)
     phases['jacobi_cycle_kernel_ms'] = sweep_ms
+    phases['jacobi_cycle_kernel_ms_each'] = sweep_in_step
     phases['flush_sharded_ms'], _ = tmax(lambda: st.flush(W))
     phases['step_minus_sweep_kernel_ms'] = ms_per_step - sweep_ms
     if detail:
@@ -837,7 +858,7 @@ def multi_gpu_leg(args, n, steps, warmup, rank, world, local_rank, peers, detail
             traffic_src = f"{ent['source']} (per rank)"
     roofline = {'kernel': ('sweep3_kernel (pipelined persistent Jacobi cycle)' if engine == 3 else 'sweep_kernel (persistent Jacobi cycle, grid barrier per pair)') + ', per GPU', 'bound': 'hbm', 'achieved': achieved,
                 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
-                'algorithmic_bytes_per_launch': algo_bytes, 'avg_launch_ms': sweep_ms, 'launches_timed': 1,
+                'algorithmic_bytes_per_launch': algo_bytes, 'avg_launch_ms': sweep_ms, 'launches_timed': len(sweep_in_step),
                 'moved_bytes_per_launch': moved, 'frac_moved': moved / (sweep_ms * 1e-3) / 1e9 / peak,
                 'frac_dram': (traffic / (sweep_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 'peak_source': peak_src,

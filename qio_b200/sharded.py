@@ -349,8 +349,12 @@ class ShardedRDM:
         audit = JA.AUDIT if audit is None else audit
         pairs = dev.to_device(pairs_np, dev.I32)
         blocks = dev.empty(max(len(pairs_np), 1), dev.BLOCK_DOUBLES) if audit else None
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
         results, summary = dev.sweep_cycle(self.gamma, self.G, Ud, W, n, pairs, mask, tables, self.a0, self.na,
                                            self.peers if self.world > 1 else None, timers=timers, blocks_out=blocks)
+        ev[1].record()
+        self.last_sweep_events = ev         # CUDA events around the kernel launch (bench.py: duration inside the timed steps)
         diag = dev.deferred_diagonals(self.gamma, self.G, W, n, inds, self.a0, self.na)
         allreduce_sum_(diag, self.group)
         _, _, _, esum = dev.orbital_entropies(diag, want_spec=False)
