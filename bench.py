@@ -537,6 +537,24 @@ def single_gpu_leg(args, n, steps, warmup, local_rank, detail):
         GR.minimize_orb_corr_GD(gamma, Gamma, inact, np.zeros(0, dtype=np.int64), max_cycle=4, thresh=0.0)
         torch.cuda.synchronize()
         phases['gd_newton_iteration_ms'] = (time.perf_counter() - t0) * 1e3 / 4
+        # BASELINE configs[1..2] (method='nr' at n = 28 and the Cr2 shape n = 86): the whole call through the public API from HOST
+        # arrays -- prep_rdm12 (H2D inside), four Newton-Raphson iterations, U / gamma / Gamma kept on the device, cost read back
+        nr = {}
+        for n_nr in (28, 86):
+            d1_nr, d2_nr = synth.solver_rdms(n_nr)
+            inact_nr = list(range(n_nr))
+
+            def nr_call():
+                g_, G_ = prep_rdm12(d1_nr, d2_nr, on_device=True)
+                out_ = GR.minimize_orb_corr_GD(g_, G_, inact_nr, np.zeros(0, dtype=np.int64), max_cycle=4, thresh=0.0)
+                torch.cuda.synchronize()
+                return out_
+            nr_call()
+            t0 = time.perf_counter()
+            nr_call()
+            nr[str(n_nr)] = {'e2e_ms_per_call_4_iterations': (time.perf_counter() - t0) * 1e3, 'iterations': 4,
+                             'h2d_bytes': int(8 * (n_nr ** 4 + n_nr ** 2))}
+        phases['nr_method_e2e'] = nr
 
     acc_mask = rs['accepted'] != 0
     algo_bytes = 16.0 * (n ** 4 - (n - 2) ** 4) * n_accepted      # bytes the reference's update touches
