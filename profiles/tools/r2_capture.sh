@@ -17,4 +17,4 @@ ncu --set full --clock-control none --import-source on -k regex:prep_tma_kernel 
 R1="python profiles/tools/rotate_profile.py 100 1"
 $R1 > $out/${tag}_plain_rot.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:rotate_tma_kernel -s 4 -c 1 -f -o $out/${tag}_rotate_n100 $R1 > $out/${tag}_ncu_rot.log 2>&1
-tail -2 $out/${tag}_plain_s100.log $out/${tag}_plain_s200.log $out/${tag}_plain_prep.log $out/${tag}_plain_rot.log; ls -la $out/${tag}_*.ncu-rep
+for f in s100 s200 prep rot; do tail -n 2 $out/${tag}_plain_$f.log; done; ls -la $out/${tag}_*.ncu-rep
