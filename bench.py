@@ -135,6 +135,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def wait_ready(self, timeout=6.0):
+        """Block until the first sample has arrived: nvidia-smi's start-up (NVML attaches to every GPU of the box) can stall
+        launches on all of them for tens of milliseconds and must be over before the timed region begins."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and self.proc.poll() is None and time.time() - t0 < timeout:
+            time.sleep(0.02)
+        time.sleep(0.1)
+
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
@@ -458,7 +466,7 @@ def single_gpu_leg(args, n, steps, warmup, local_rank, detail):
     # ---- timed: device-resident -----------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.3)
+    sampler.wait_ready()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     del sweep_events[:]
@@ -792,22 +800,28 @@ def multi_gpu_leg(args, n, steps, warmup, rank, world, local_rank, peers, detail
                       'unexplained': len(audit['unexplained']), 'min_fine_margin': audit['min_fine_margin'],
                       'min_coarse_margin': audit['min_coarse_margin']}
 
+    step_ms_each = []
+
     def timed_steps(dm1_in, dm2_in, k):
         sampler = ClockSampler(local_rank)
         sampler.start()
-        time.sleep(0.5)
+        sampler.wait_ready()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
         torch.cuda.synchronize()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
         e0.record()
-        for _ in range(k):
+        marks[0].record()
+        for q in range(k):
             step(dm1_in, dm2_in)
+            marks[q + 1].record()
         e1.record()
         torch.cuda.synchronize()
         dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+        ms = torch.tensor([e0.elapsed_time(e1)] + [marks[q].elapsed_time(marks[q + 1]) for q in range(k)], dtype=torch.float64, device='cuda')
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / k, sampler.stop()
+        step_ms_each.append([float(x) for x in ms[1:].tolist()])        # diagnostics: every step of the timed region, max over ranks
+        return float(ms[0].item()) / k, sampler.stop()
 
     del sweep_events[:]
     ms_per_step, clocks = timed_steps(dm1_d, dm2_d, steps)
@@ -853,6 +867,7 @@ def multi_gpu_leg(args, n, steps, warmup, rank, world, local_rank, peers, detail
     sweep_ms = float(np.mean(sweep_in_step))               # average launch duration over the timed steps (max over ranks each)
     phases['jacobi_cycle_kernel_ms'] = sweep_ms
     phases['jacobi_cycle_kernel_ms_each'] = sweep_in_step
+    phases['step_ms_each'] = step_ms_each[0] if step_ms_each else None
     phases['flush_sharded_ms'], _ = tmax(lambda: st.flush(W))
     phases['step_minus_sweep_kernel_ms'] = ms_per_step - sweep_ms
     if detail:
